@@ -1,0 +1,200 @@
+"""ctypes bindings for the CPU oracle (libtv5_oracle.so) and, when built, for the compiled
+copies of the reference under oracle/_ref/ (see build_ref.sh).  TEST INFRASTRUCTURE."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_bp = C.POINTER(C.c_uint8)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libtv5_oracle.so")
+    src = os.path.join(_HERE, "tv5_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libtv5_oracle.so"])
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.tv5o_sampson_err.restype = C.c_double
+        L.tv5o_sampson_err.argtypes = [_dp, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.tv5o_score.restype = None
+        L.tv5o_score.argtypes = [_dp, _dp, C.c_int, _dp, C.c_int, C.c_double, _ip, _bp]
+        L.tv5o_solve5.restype = C.c_int
+        L.tv5o_solve5.argtypes = [_dp, _dp, _dp, _dp]
+        L.tv5o_nullspace_basis.restype = None
+        L.tv5o_nullspace_basis.argtypes = [_dp, _dp, _dp]
+        L.tv5o_hidden_poly.restype = None
+        L.tv5o_hidden_poly.argtypes = [_dp, _dp, _dp]
+        L.tv5o_real_roots.restype = C.c_int
+        L.tv5o_real_roots.argtypes = [_dp, C.c_int, _dp]
+        L.tv5o_cheirality.restype = C.c_int
+        L.tv5o_cheirality.argtypes = [_dp, _dp, _dp, C.c_int, _dp]
+        L.tv5o_index_from_uniform.restype = C.c_int32
+        L.tv5o_index_from_uniform.argtypes = [C.c_float, C.c_int]
+        L.tv5o_ransac.restype = C.c_int
+        L.tv5o_ransac.argtypes = [_dp, _dp, C.c_int, _ip, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_double, C.c_int, _dp, _dp, _ip, _ip, _bp]
+        L.tv5o_solve_sets.restype = None
+        L.tv5o_solve_sets.argtypes = [_dp, _dp, _ip, C.c_int, C.c_int, _dp, _dp, _ip, _ip]
+        _lib = L
+    return _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def sampson_err(E, x1, y1, x2, y2):
+    E = _f64(E).reshape(9)
+    return lib().tv5o_sampson_err(_p(E, _dp), float(x1), float(y1), float(x2), float(y2))
+
+
+def score(x1, x2, E_list, thr, n=None, want_mask=False):
+    """counts[M] (and mask[M,n]) of the reference Sampson test on the first n points."""
+    x1, x2 = _f64(x1), _f64(x2)
+    E_list = _f64(E_list).reshape(-1, 9)
+    n = x1.shape[0] if n is None else int(n)
+    M = E_list.shape[0]
+    counts = np.zeros(M, np.int32)
+    mask = np.zeros((M, n), np.uint8) if want_mask else None
+    lib().tv5o_score(_p(x1, _dp), _p(x2, _dp), n, _p(E_list, _dp), M, float(thr),
+                     _p(counts, _ip), _p(mask, _bp))
+    return (counts, mask) if want_mask else counts
+
+
+def solve5(q, qp):
+    """(E[n,3,3], w[n]) for one minimal set; q, qp are 5x2."""
+    q, qp = _f64(q).reshape(5, 2), _f64(qp).reshape(5, 2)
+    E = np.zeros((10, 9))
+    w = np.zeros(10)
+    n = lib().tv5o_solve5(_p(q, _dp), _p(qp, _dp), _p(E, _dp), _p(w, _dp))
+    return E[:n].reshape(n, 3, 3).copy(), w[:n].copy()
+
+
+def nullspace_basis(q, qp):
+    q, qp = _f64(q).reshape(5, 2), _f64(qp).reshape(5, 2)
+    B = np.zeros((4, 9))
+    lib().tv5o_nullspace_basis(_p(q, _dp), _p(qp, _dp), _p(B, _dp))
+    return B
+
+
+def hidden_poly(q, qp):
+    q, qp = _f64(q).reshape(5, 2), _f64(qp).reshape(5, 2)
+    p = np.zeros(11)
+    lib().tv5o_hidden_poly(_p(q, _dp), _p(qp, _dp), _p(p, _dp))
+    return p
+
+
+def real_roots(p):
+    p = _f64(p)
+    r = np.zeros(32)
+    n = lib().tv5o_real_roots(_p(p, _dp), len(p) - 1, _p(r, _dp))
+    return r[:n].copy()
+
+
+def cheirality(q, qp, E):
+    """(E_kept[n,3,3], P[n,3,4]) after the unanimous 5-point vote."""
+    q, qp = _f64(q).reshape(5, 2), _f64(qp).reshape(5, 2)
+    Eb = np.zeros((10, 9))
+    E = _f64(E).reshape(-1, 9)
+    Eb[: len(E)] = E
+    P = np.zeros((10, 12))
+    n = lib().tv5o_cheirality(_p(q, _dp), _p(qp, _dp), _p(Eb, _dp), len(E), _p(P, _dp))
+    return Eb[:n].reshape(n, 3, 3).copy(), P[:n].reshape(n, 3, 4).copy()
+
+
+def index_from_uniform(u, N):
+    return lib().tv5o_index_from_uniform(float(np.float32(u)), int(N))
+
+
+def solve_sets(x1, x2, sets, with_cheirality=True):
+    x1, x2, sets = _f64(x1), _f64(x2), _i32(sets).reshape(-1, 5)
+    H = sets.shape[0]
+    E = np.zeros((H, 10, 9))
+    P = np.zeros((H, 10, 12))
+    nr = np.zeros(H, np.int32)
+    nv = np.zeros(H, np.int32)
+    lib().tv5o_solve_sets(_p(x1, _dp), _p(x2, _dp), _p(sets, _ip), H, int(with_cheirality),
+                          _p(E, _dp), _p(P, _dp), _p(nr, _ip), _p(nv, _ip))
+    return dict(E=E, P=P, n_roots=nr, n_valid=nv)
+
+
+def ransac(x1, x2, sets, iters, thr, n_pre=None, n_full=None, with_cheirality=True,
+           want_mask=False):
+    """Reference-order RANSAC over sets[H,5] with H = n_threads*iters."""
+    x1, x2, sets = _f64(x1), _f64(x2), _i32(sets).reshape(-1, 5)
+    N = x1.shape[0]
+    H = sets.shape[0]
+    assert H % iters == 0
+    n_pre = N if n_pre is None else int(n_pre)
+    n_full = N if n_full is None else int(n_full)
+    E = np.zeros(9)
+    P = np.zeros(12)
+    bs = np.zeros(1, np.int32)
+    br = np.zeros(1, np.int32)
+    mask = np.zeros(n_full, np.uint8) if want_mask else None
+    cnt = lib().tv5o_ransac(_p(x1, _dp), _p(x2, _dp), N, _p(sets, _ip), H // iters, int(iters),
+                            n_pre, n_full, float(thr), int(with_cheirality), _p(E, _dp),
+                            _p(P, _dp), _p(bs, _ip), _p(br, _ip), _p(mask, _bp))
+    out = dict(E=E.reshape(3, 3), P=P.reshape(3, 4), count=int(cnt), best_set=int(bs[0]),
+               best_root=int(br[0]))
+    if want_mask:
+        out["mask"] = mask
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Compiled copies of the reference (oracle/_ref/, built by build_ref.sh).  Optional.
+# ---------------------------------------------------------------------------------------------
+_REF = os.path.join(_HERE, "_ref")
+_ref_host = None
+
+
+def ref_host_available():
+    return os.path.exists(os.path.join(_REF, "libref_host.so"))
+
+
+def ref_host():
+    global _ref_host
+    if _ref_host is None:
+        L = C.CDLL(os.path.join(_REF, "libref_host.so"))
+        L.ref_solve_sets.restype = C.c_int
+        L.ref_solve_sets.argtypes = [_dp, _dp, C.c_int, _ip, C.c_int, _dp, _ip, _dp, _dp, _ip]
+        _ref_host = L
+    return _ref_host
+
+
+def ref_solve_sets(x1, x2, sets):
+    """The reference's own compute_E_matrices_optimized + compute_P_matrices, host-compiled."""
+    x1, x2, sets = _f64(x1), _f64(x2), _i32(sets).reshape(-1, 5)
+    H = sets.shape[0]
+    E_all = np.zeros((H, 10, 9))
+    E_valid = np.zeros((H, 10, 9))
+    P_valid = np.zeros((H, 10, 12))
+    nr = np.zeros(H, np.int32)
+    nv = np.zeros(H, np.int32)
+    rc = ref_host().ref_solve_sets(_p(x1, _dp), _p(x2, _dp), x1.shape[0], _p(sets, _ip), H,
+                                   _p(E_all, _dp), _p(nr, _ip), _p(E_valid, _dp),
+                                   _p(P_valid, _dp), _p(nv, _ip))
+    assert rc == 0
+    return dict(E_all=E_all, n_roots=nr, E=E_valid, P=P_valid, n_valid=nv)
