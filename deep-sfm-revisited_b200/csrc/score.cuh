@@ -1,0 +1,102 @@
+// score.cuh — Sampson inlier scoring of hypotheses against correspondences.
+//
+// Two scorers:
+//   * sampson_exact(): float64, the reference's exact operation order
+//     (RANSAC_FiveP/essential_matrix/kernel_functions.cu:231-264 as compiled by nvcc 12.9 for
+//     sm_100a) — bit-identical inlier decisions.
+//   * score_bounds_kernel: float32 guard-band scorer on packed FFMA2 (fma.rn.f32x2), the
+//     roofline kernel.  For each (hypothesis, point) it classifies the evaluation as
+//     sure-inlier / sure-outlier / undecidable under a rigorous rounding-error bound and
+//     accumulates   notin[m] = #{not sure-inlier},  out[m] = #{sure-outlier}.
+//     Then  n - notin[m] <= exact count[m] <= n - out[m].
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tv5 {
+
+// ------------------------------------------------------------------------------------------
+// exact float64 decision (explicit _rn intrinsics: no re-association, no other contraction)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sampson_err_exact(const double (&E)[9], double x1, double y1,
+                                                    double x2, double y2) {
+  const double Ex0 = __dadd_rn(__fma_rn(E[1], y1, __dmul_rn(E[0], x1)), E[2]);
+  const double Ex1 = __dadd_rn(__fma_rn(E[4], y1, __dmul_rn(E[3], x1)), E[5]);
+  const double Ex2 = __dadd_rn(__fma_rn(E[7], y1, __dmul_rn(E[6], x1)), E[8]);
+  const double tE0 = __dadd_rn(__fma_rn(E[3], y2, __dmul_rn(E[0], x2)), E[6]);
+  const double tE1 = __dadd_rn(__fma_rn(E[4], y2, __dmul_rn(E[1], x2)), E[7]);
+  const double num = __dadd_rn(Ex2, __fma_rn(y2, Ex1, __dmul_rn(x2, Ex0)));
+  const double den = __fma_rn(tE1, tE1, __fma_rn(tE0, tE0, __fma_rn(Ex0, Ex0, __dmul_rn(Ex1, Ex1))));
+  return fabs(__ddiv_rn(num, __dsqrt_rn(den)));
+}
+
+__device__ __forceinline__ bool sampson_inlier_exact(const double (&E)[9], double x1, double y1,
+                                                     double x2, double y2, double thr) {
+  return sampson_err_exact(E, x1, y1, x2, y2) <= thr;  // NaN -> outlier, as the reference
+}
+
+// ------------------------------------------------------------------------------------------
+// float32 guard-band scorer
+// ------------------------------------------------------------------------------------------
+// Hypothesis record: E^ = E/||E||_F;  rows 0,1 as is, row 2 scaled by 1/thr (g), plus the two
+// unscaled row-2 entries needed by E^T x2.
+struct __align__(16) Hyp32 {
+  float e00, e01, e02, e10, e11, e12, g0, g1, g2, e20, e21, pad;
+};
+static_assert(sizeof(Hyp32) == 48, "Hyp32 layout");
+
+// Point-pair record (two consecutive correspondences p, q packed lane-wise for f32x2 math):
+//   [x1p x1q y1p y1q] [x2p x2q y2p y2q] [x2p/thr x2q/thr y2p/thr y2q/thr]
+struct __align__(16) PointPair32 {
+  float2 x1, y1, x2, y2, x2s, y2s;
+};
+static_assert(sizeof(PointPair32) == 48, "PointPair32 layout");
+
+// Per image-pair constants of the bound (see DESIGN.md "guard band"):
+//   uncertain  <=>  | n'^2 - d |  <=  c n'^2 + K ,   n' = num/thr, d = den (unit-norm E^)
+struct BandConst {
+  float neg_one_plus_c;   // -(1 + c)
+  float neg_one_minus_c;  // -(1 - c)
+  float neg_K;            // -K
+  float two_K;            // 2K
+};
+
+struct HypRegs {  // one hypothesis with every coefficient duplicated in both f32x2 lanes
+  float2 e00, e01, e02, e10, e11, e12, g0, g1, g2, e20, e21;
+};
+
+__device__ __forceinline__ float2 dup(float v) { return make_float2(v, v); }
+
+__device__ __forceinline__ void load_hyp(HypRegs& h, const Hyp32& s) {
+  h.e00 = dup(s.e00); h.e01 = dup(s.e01); h.e02 = dup(s.e02);
+  h.e10 = dup(s.e10); h.e11 = dup(s.e11); h.e12 = dup(s.e12);
+  h.g0 = dup(s.g0); h.g1 = dup(s.g1); h.g2 = dup(s.g2);
+  h.e20 = dup(s.e20); h.e21 = dup(s.e21);
+}
+
+// 20 packed FP32 instructions for two (hypothesis, point) evaluations + 4 sign-bit adds.
+__device__ __forceinline__ void eval_pair(const HypRegs& h, const PointPair32& p, float2 nc1,
+                                          float2 nc2, float2 negK, float2 twoK, uint32_t& notin,
+                                          uint32_t& out, bool both_lanes = true) {
+  const float2 Ex0 = __ffma2_rn(h.e00, p.x1, __ffma2_rn(h.e01, p.y1, h.e02));
+  const float2 Ex1 = __ffma2_rn(h.e10, p.x1, __ffma2_rn(h.e11, p.y1, h.e12));
+  const float2 Ex2 = __ffma2_rn(h.g0, p.x1, __ffma2_rn(h.g1, p.y1, h.g2));
+  const float2 tE0 = __ffma2_rn(h.e00, p.x2, __ffma2_rn(h.e10, p.y2, h.e20));
+  const float2 tE1 = __ffma2_rn(h.e01, p.x2, __ffma2_rn(h.e11, p.y2, h.e21));
+  const float2 n = __ffma2_rn(p.x2s, Ex0, __ffma2_rn(p.y2s, Ex1, Ex2));
+  const float2 nn = __fmul2_rn(n, n);
+  float2 dK = __ffma2_rn(Ex0, Ex0, negK);  // d - K
+  dK = __ffma2_rn(Ex1, Ex1, dK);
+  dK = __ffma2_rn(tE0, tE0, dK);
+  dK = __ffma2_rn(tE1, tE1, dK);
+  const float2 lo = __ffma2_rn(nn, nc1, dK);                     // d - K - (1+c) n'^2  (< 0: not sure-in)
+  const float2 hi = __fadd2_rn(__ffma2_rn(nn, nc2, dK), twoK);   // d + K - (1-c) n'^2  (< 0: sure-out)
+  notin += __float_as_uint(lo.x) >> 31;
+  out += __float_as_uint(hi.x) >> 31;
+  if (both_lanes) {
+    notin += __float_as_uint(lo.y) >> 31;
+    out += __float_as_uint(hi.y) >> 31;
+  }
+}
+
+}  // namespace tv5

@@ -1,0 +1,1099 @@
+// tv5.cu — kernels and C ABI of libtv5 (see include/tv5.h).  sm_100a only.
+//
+// Pipeline of one submission (B image pairs, everything stream-ordered, no host sync):
+//   prep_points     float64 [N,2] x2  ->  packed float32 point pairs + per-pair norm bounds
+//   solve_sets      one minimal set per thread (solve5.cuh) -> E/P lists + float32 hypotheses
+//   plan_tiles      per-pair guard-band constants, scoring tile table (single CTA)
+//   score_bounds    float32 FFMA2 guard-band scorer (the roofline kernel), persistent CTAs,
+//                   correspondence tiles staged in shared memory by cp.async.bulk (TMA)
+//   pick_candidates hypotheses whose upper bound reaches the best lower bound
+//   exact_counts    float64 re-score of the candidates with the reference's exact sequence
+//   finalize        first-max selection (count desc, hypothesis id asc), E/P/mask output
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "solve5.cuh"
+#include "tv5_internal.h"
+
+namespace tv5 {
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                          uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    T w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w > v ? w : v;
+  }
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// prep_points: grid (ceil(max_pp / 256), B)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_points(const PairDesc* __restrict__ desc,
+                                                   PairState* __restrict__ state,
+                                                   PointPair32* __restrict__ pp, double inv_thr) {
+  const PairDesc d = desc[blockIdx.y];
+  const int npp = (d.n + 1) >> 1;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  float r1 = 0.f, r2 = 0.f;
+  int bad = 0;
+  if (g < npp) {
+    const int p = 2 * g, q = min(2 * g + 1, d.n - 1);
+    const double2 a1 = reinterpret_cast<const double2*>(d.x1)[p];
+    const double2 b1 = reinterpret_cast<const double2*>(d.x1)[q];
+    const double2 a2 = reinterpret_cast<const double2*>(d.x2)[p];
+    const double2 b2 = reinterpret_cast<const double2*>(d.x2)[q];
+    PointPair32 o;
+    o.x1 = make_float2((float)a1.x, (float)b1.x);
+    o.y1 = make_float2((float)a1.y, (float)b1.y);
+    o.x2 = make_float2((float)a2.x, (float)b2.x);
+    o.y2 = make_float2((float)a2.y, (float)b2.y);
+    o.x2s = make_float2((float)(a2.x * inv_thr), (float)(b2.x * inv_thr));
+    o.y2s = make_float2((float)(a2.y * inv_thr), (float)(b2.y * inv_thr));
+    pp[d.pp_off + g] = o;
+    const double s1 = fmax(a1.x * a1.x + a1.y * a1.y, b1.x * b1.x + b1.y * b1.y) + 1.0;
+    const double s2 = fmax(a2.x * a2.x + a2.y * a2.y, b2.x * b2.x + b2.y * b2.y) + 1.0;
+    bad = !(s1 < 1e30) || !(s2 < 1e30);  // catches NaN and Inf as well
+    r1 = __double2float_ru(s1);
+    r2 = __double2float_ru(s2);
+  }
+  r1 = warp_max(bad ? 0.f : r1);
+  r2 = warp_max(bad ? 0.f : r2);
+  bad = __any_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&state[blockIdx.y].r1_bits, __float_as_uint(r1));
+    atomicMax(&state[blockIdx.y].r2_bits, __float_as_uint(r2));
+    if (bad) atomicOr(&state[blockIdx.y].nonfinite, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// solve_sets: one thread per minimal set, grid (ceil(H/64), B), block 64
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void make_hyp32(const double* E, double inv_thr, Hyp32& h) {
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) s += E[i] * E[i];
+  const double f = 1.0 / sqrt(s);
+  h.e00 = (float)(E[0] * f); h.e01 = (float)(E[1] * f); h.e02 = (float)(E[2] * f);
+  h.e10 = (float)(E[3] * f); h.e11 = (float)(E[4] * f); h.e12 = (float)(E[5] * f);
+  h.g0 = (float)(E[6] * f * inv_thr); h.g1 = (float)(E[7] * f * inv_thr);
+  h.g2 = (float)(E[8] * f * inv_thr);
+  h.e20 = (float)(E[6] * f); h.e21 = (float)(E[7] * f);
+  h.pad = 0.f;
+}
+
+__global__ void __launch_bounds__(64) solve_sets(const PairDesc* __restrict__ desc,
+                                                 PairState* __restrict__ state, int H,
+                                                 int with_cheirality, double inv_thr,
+                                                 double* __restrict__ E_list,
+                                                 double* __restrict__ P_list,
+                                                 int32_t* __restrict__ n_valid,
+                                                 int32_t* __restrict__ n_roots,
+                                                 Hyp32* __restrict__ hyp,
+                                                 int32_t* __restrict__ hyp_id,
+                                                 uint32_t* __restrict__ notin,
+                                                 uint32_t* __restrict__ out) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const int b = blockIdx.y;
+  const PairDesc d = desc[b];
+  double q[5][2], qp[5][2];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    int idx = d.sets[5 * (size_t)h + i];
+    idx = max(0, min(idx, d.n - 1));
+    const double2 a = reinterpret_cast<const double2*>(d.x1)[idx];
+    const double2 c = reinterpret_cast<const double2*>(d.x2)[idx];
+    q[i][0] = a.x; q[i][1] = a.y;
+    qp[i][0] = c.x; qp[i][1] = c.y;
+  }
+  const size_t s = (size_t)b * H + h;
+  double* E = E_list + s * 90;
+  double* P = P_list ? P_list + s * 120 : nullptr;
+  int nr = 0;
+  const int nv = solve_minimal_set(q, qp, with_cheirality != 0, E, P, &nr);
+  n_valid[s] = nv;
+  if (n_roots) n_roots[s] = nr;
+  if (hyp && nv > 0) {
+    const int base = atomicAdd(&state[b].M, nv);
+    const size_t o = (size_t)b * H * 10 + base;
+    for (int j = 0; j < nv; ++j) {
+      Hyp32 r;
+      make_hyp32(E + 9 * j, inv_thr, r);
+      hyp[o + j] = r;
+      hyp_id[o + j] = h * 16 + j;
+      notin[o + j] = 0u;
+      out[o + j] = 0u;
+    }
+  }
+}
+
+// float32 hypothesis records for an arbitrary E list (tv5_score_bounds)
+__global__ void hyps_from_list(const double* __restrict__ E_list, int M, double inv_thr,
+                               PairState* state, Hyp32* __restrict__ hyp, int32_t* hyp_id,
+                               uint32_t* notin, uint32_t* out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m == 0) state[0].M = M;
+  if (m >= M) return;
+  Hyp32 r;
+  make_hyp32(E_list + 9 * (size_t)m, inv_thr, r);
+  hyp[m] = r;
+  hyp_id[m] = m;
+  notin[m] = 0u;
+  out[m] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan_tiles: one CTA.  Guard-band constants (DESIGN.md "guard band") and the tile table.
+//   computed n' = num/thr has |error| <= Bn = 8.2 u R1 R2 / thr   (u = 2^-24, ||E^||_F = 1,
+//   R1 = max||(x1,1)||, R2 = max||(x2,1)||), sqrt(d) has |error| <= Bd = 18 u max(R1,R2).
+//   With B = 1.02 (Bn + Bd):  sure-in  <=  (|n'|+B)^2 <= d,  sure-out  <=  (|n'|-B)^2 > d, and
+//   2 B |n'| <= c n'^2 + B^2/c  gives the multiply-add form used by eval_pair.
+// ------------------------------------------------------------------------------------------
+__global__ void plan_tiles(const PairDesc* __restrict__ desc, PairState* __restrict__ state,
+                           Control* __restrict__ ctl, int B, int pp_per_tile, double thr,
+                           int allow_fast) {
+  if (threadIdx.x != 0) return;
+  int total = 0;
+  for (int b = 0; b < B; ++b) {
+    PairState& s = state[b];
+    const PairDesc& d = desc[b];
+    const double u = 5.9604644775390625e-8;
+    const double R1 = sqrt((double)__uint_as_float(s.r1_bits));
+    const double R2 = sqrt((double)__uint_as_float(s.r2_bits));
+    const double Bn = 8.2 * u * R1 * R2 / thr;
+    const double Bd = 18.0 * u * fmax(R1, R2);
+    const double Bt = 1.02 * (Bn + Bd);
+    int fast = allow_fast && !s.nonfinite && d.n_pre == d.n_full && (R1 < 1024.0) &&
+               (R2 < 1024.0) && (Bt < 0.125) && (Bt > 0.0);
+    double c = fmin(0.25, fmax(3.0 * Bt, 1.0 / 1024.0));
+    const double K = 1.02 * Bt * Bt * (1.0 + 1.0 / c);
+    c += 16.0 * u;  // covers the rounding of the final lo/hi evaluations themselves
+    s.band.neg_one_plus_c = -(float)(1.0 + c);
+    s.band.neg_one_minus_c = -__double2float_rd(1.0 - c);
+    s.band.neg_K = -__double2float_ru(K);
+    s.band.two_K = __double2float_ru(2.0 * K) * 1.000001f;
+    s.fast = fast;
+    s.tile_start = total;
+    const int npp = (d.n_full + 1) >> 1;
+    s.n_hc = (s.M + kHypChunk - 1) / kHypChunk;
+    s.n_pc = (npp + pp_per_tile - 1) / pp_per_tile;
+    if (fast) total += s.n_hc * s.n_pc;
+  }
+  ctl->n_tiles = total;
+  ctl->tile_counter = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// score_bounds: persistent CTAs pulling (pair, hypothesis chunk, point chunk) tiles.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScoreThreads, 2)
+score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ state,
+             Control* __restrict__ ctl, int B, int H, int pp_per_tile,
+             const PointPair32* __restrict__ pp, const Hyp32* __restrict__ hyp,
+             uint32_t* __restrict__ notin, uint32_t* __restrict__ out) {
+  __shared__ __align__(128) PointPair32 tile[kMaxTilePairs];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_tile;
+  const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t phase = 0;
+  const int n_tiles = ctl->n_tiles;
+  for (;;) {
+    if (tid == 0) s_tile = atomicAdd(&ctl->tile_counter, 1);
+    __syncthreads();
+    const int t = s_tile;
+    if (t >= n_tiles) break;
+    // locate the image pair (tile_start is ascending; slow pairs contribute no tiles)
+    int lo = 0, hi = B - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (state[mid].tile_start <= t) lo = mid; else hi = mid - 1;
+    }
+    int b = lo;
+    while (!state[b].fast || state[b].n_hc * state[b].n_pc == 0) --b;  // skip empty entries
+    const PairState& s = state[b];
+    const PairDesc& d = desc[b];
+    const int lt = t - s.tile_start;
+    const int hc = lt / s.n_pc, pc = lt - hc * s.n_pc;
+    const int npp_all = (d.n_full + 1) >> 1;
+    const int pp0 = pc * pp_per_tile;
+    const int npp = min(pp_per_tile, npp_all - pp0);
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)npp * (uint32_t)sizeof(PointPair32);
+      mbar_expect_tx(&bar, bytes);
+      bulk_load(tile, pp + d.pp_off + pp0, bytes, &bar);
+    }
+    // hypotheses of this thread (registers), loaded while the bulk copy is in flight
+    const size_t hbase = (size_t)b * H * 10 + (size_t)hc * kHypChunk;
+    HypRegs hr[kHypPerThread];
+    bool live[kHypPerThread];
+#pragma unroll
+    for (int k = 0; k < kHypPerThread; ++k) {
+      const int m = hc * kHypChunk + k * kScoreThreads + tid;
+      live[k] = m < s.M;
+      Hyp32 raw;
+      if (live[k]) {
+        const float4* src = reinterpret_cast<const float4*>(hyp + hbase + k * kScoreThreads + tid);
+        float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2);
+        raw.e00 = v0.x; raw.e01 = v0.y; raw.e02 = v0.z; raw.e10 = v0.w;
+        raw.e11 = v1.x; raw.e12 = v1.y; raw.g0 = v1.z; raw.g1 = v1.w;
+        raw.g2 = v2.x; raw.e20 = v2.y; raw.e21 = v2.z; raw.pad = 0.f;
+      } else {
+        raw = Hyp32{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      }
+      load_hyp(hr[k], raw);
+    }
+    const float2 nc1 = dup(s.band.neg_one_plus_c), nc2 = dup(s.band.neg_one_minus_c);
+    const float2 negK = dup(s.band.neg_K), twoK = dup(s.band.two_K);
+    uint32_t a[kHypPerThread], o[kHypPerThread];
+#pragma unroll
+    for (int k = 0; k < kHypPerThread; ++k) { a[k] = 0u; o[k] = 0u; }
+
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+    // the very last point pair of an odd-sized image pair holds a duplicated point in lane .y
+    const bool odd_tail = (pp0 + npp == npp_all) && (d.n_full & 1);
+    const int nfull = odd_tail ? npp - 1 : npp;
+#pragma unroll 2
+    for (int i = 0; i < nfull; ++i) {
+      const PointPair32 p = tile[i];
+#pragma unroll
+      for (int k = 0; k < kHypPerThread; ++k) eval_pair(hr[k], p, nc1, nc2, negK, twoK, a[k], o[k]);
+    }
+    if (odd_tail) {
+      const PointPair32 p = tile[nfull];
+#pragma unroll
+      for (int k = 0; k < kHypPerThread; ++k)
+        eval_pair(hr[k], p, nc1, nc2, negK, twoK, a[k], o[k], false);
+    }
+#pragma unroll
+    for (int k = 0; k < kHypPerThread; ++k)
+      if (live[k]) {
+        const size_t slot = hbase + k * kScoreThreads + tid;
+        if (a[k]) atomicAdd(&notin[slot], a[k]);
+        if (o[k]) atomicAdd(&out[slot], o[k]);
+      }
+    __syncthreads();  // everyone is done with `tile` and `s_tile` before the next round
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pick_candidates: one CTA per image pair
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pick_candidates(const PairDesc* __restrict__ desc,
+                                                       PairState* __restrict__ state, int H,
+                                                       const uint32_t* __restrict__ notin,
+                                                       const uint32_t* __restrict__ out,
+                                                       int32_t* __restrict__ cand,
+                                                       int32_t* __restrict__ cand_cnt) {
+  const int b = blockIdx.x;
+  PairState& s = state[b];
+  const int M = s.M;
+  const size_t base = (size_t)b * H * 10;
+  __shared__ int s_best[8];
+  __shared__ int s_L;
+  if (!s.fast) {  // float64 path: every hypothesis is a candidate
+    for (int m = threadIdx.x; m < M; m += blockDim.x) { cand[base + m] = m; cand_cnt[base + m] = 0; }
+    if (threadIdx.x == 0) s.n_cand = M;
+    return;
+  }
+  const int n = desc[b].n_full;
+  int best = 0;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) best = max(best, n - (int)notin[base + m]);
+  best = warp_max(best);
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int L = 0;
+    for (int w = 0; w < 8; ++w) L = max(L, s_best[w]);
+    s_L = max(L, 1);  // a hypothesis that cannot have a single inlier never wins
+  }
+  __syncthreads();
+  const int L = s_L;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const int hi = n - (int)out[base + m];
+    if (hi >= L) {
+      const int i = atomicAdd(&s.n_cand, 1);
+      cand[base + i] = m;
+      cand_cnt[base + i] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// exact_counts: float64 re-score of the candidates.  grid (X, B); work item = (candidate,
+// chunk of kExactChunk points), strided over X CTAs.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) exact_counts(const PairDesc* __restrict__ desc,
+                                                    const PairState* __restrict__ state, int H,
+                                                    double thr, const double* __restrict__ E_list,
+                                                    const int32_t* __restrict__ hyp_id,
+                                                    const int32_t* __restrict__ cand,
+                                                    int32_t* __restrict__ cand_cnt) {
+  const int b = blockIdx.y;
+  const PairDesc d = desc[b];
+  const int n_cand = state[b].n_cand;
+  const int n = d.n_full;
+  const int n_chunks = (n + kExactChunk - 1) / kExactChunk;
+  const size_t base = (size_t)b * H * 10;
+  __shared__ int s_part[8];
+  for (int item = blockIdx.x; item < n_cand * n_chunks; item += gridDim.x) {
+    const int ci = item / n_chunks, ch = item - ci * n_chunks;
+    const int id = hyp_id[base + cand[base + ci]];
+    const double* Eg = E_list + ((size_t)b * H + (id >> 4)) * 90 + (id & 15) * 9;
+    double E[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) E[i] = Eg[i];
+    int c = 0;
+    const int k1 = min(n, (ch + 1) * kExactChunk);
+    for (int k = ch * kExactChunk + threadIdx.x; k < k1; k += blockDim.x) {
+      const double2 p1 = reinterpret_cast<const double2*>(d.x1)[k];
+      const double2 p2 = reinterpret_cast<const double2*>(d.x2)[k];
+      c += sampson_inlier_exact(E, p1.x, p1.y, p2.x, p2.y, thr) ? 1 : 0;
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += s_part[w];
+      if (t) atomicAdd(&cand_cnt[base + ci], t);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: first-max selection + outputs.  One CTA per image pair.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finalize(const PairDesc* __restrict__ desc,
+                                                const PairState* __restrict__ state, int H,
+                                                double thr, const double* __restrict__ E_list,
+                                                const double* __restrict__ P_list,
+                                                const int32_t* __restrict__ hyp_id,
+                                                const int32_t* __restrict__ cand,
+                                                const int32_t* __restrict__ cand_cnt) {
+  const int b = blockIdx.x;
+  const PairDesc d = desc[b];
+  const PairState& s = state[b];
+  const size_t base = (size_t)b * H * 10;
+  __shared__ unsigned long long s_key[8];
+  __shared__ unsigned long long s_win;
+  unsigned long long key = 0ull;
+  for (int i = threadIdx.x; i < s.n_cand; i += blockDim.x) {
+    const uint32_t cnt = (uint32_t)cand_cnt[base + i];
+    const uint32_t id = (uint32_t)hyp_id[base + cand[base + i]];
+    const unsigned long long k = ((unsigned long long)cnt << 32) | (0xFFFFFFFFu - id);
+    key = k > key ? k : key;
+  }
+  key = warp_max(key);
+  if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long w = 0ull;
+    for (int i = 0; i < 8; ++i) w = s_key[i] > w ? s_key[i] : w;
+    s_win = w;
+  }
+  __syncthreads();
+  const unsigned long long win = s_win;
+  const int count = (int)(win >> 32);
+  const int id = (int)(0xFFFFFFFFu - (uint32_t)(win & 0xFFFFFFFFull));
+  const bool have = count > 0;
+  const int sid = have ? id : 0;
+  const double* Eg = E_list + ((size_t)b * H + (sid >> 4)) * 90 + (sid & 15) * 9;
+  if (threadIdx.x < 9) d.E_out[threadIdx.x] = have ? Eg[threadIdx.x] : 0.0;
+  if (d.P_out && threadIdx.x < 12) {
+    const double* Pg = P_list ? P_list + ((size_t)b * H + (sid >> 4)) * 120 + (sid & 15) * 12 : nullptr;
+    d.P_out[threadIdx.x] = (have && Pg) ? Pg[threadIdx.x] : 0.0;
+  }
+  if (threadIdx.x == 0) {
+    tv5_result r;
+    r.count = count;
+    r.best_set = have ? (id >> 4) : -1;
+    r.best_root = have ? (id & 15) : -1;
+    r.n_hypotheses = s.M;
+    r.n_candidates = s.n_cand;
+    r.fast_path = s.fast;
+    r.reserved[0] = r.reserved[1] = 0;
+    *d.result = r;
+  }
+  if (d.mask_out) {
+    double E[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) E[i] = have ? Eg[i] : 0.0;
+    for (int k = threadIdx.x; k < d.n_full; k += blockDim.x) {
+      const double2 p1 = reinterpret_cast<const double2*>(d.x1)[k];
+      const double2 p2 = reinterpret_cast<const double2*>(d.x2)[k];
+      d.mask_out[k] = (have && sampson_inlier_exact(E, p1.x, p1.y, p2.x, p2.y, thr)) ? 1 : 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// general two-stage selection (n_pre != n_full): float64 only.
+//   stage A  counts of every hypothesis on the first n_pre points     (exact_counts)
+//   per set  best root = first maximum                                (set_winners)
+//   stage B  counts of the per-set winners on the first n_full points (exact_counts)
+//   finalize first maximum over sets
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) set_winners(PairDesc* __restrict__ desc,
+                                                   PairState* __restrict__ state, int H,
+                                                   const int32_t* __restrict__ hyp_id,
+                                                   int32_t* __restrict__ cand,
+                                                   int32_t* __restrict__ cand_cnt,
+                                                   int32_t* __restrict__ scratch) {
+  // Stage A left cand[i] = i (all hypotheses) and cand_cnt[i] = count on n_pre points.
+  // A hypothesis survives if no hypothesis of the same set has a larger count, or an equal
+  // count and a smaller root index.  Hypotheses of one set occupy consecutive slots.
+  const int b = blockIdx.x;
+  PairState& s = state[b];
+  const size_t base = (size_t)b * H * 10;
+  const size_t sbase = (size_t)b * H * 20;  // scratch: [H*10] flags + [H*10] compacted list
+  const int M = s.M;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const int id = hyp_id[base + m], set = id >> 4, root = id & 15, cnt = cand_cnt[base + m];
+    bool win = true;
+    for (int j = m - root; j < M && j <= m - root + 9; ++j) {
+      if (j == m || j < 0) continue;
+      const int jd = hyp_id[base + j];
+      if ((jd >> 4) != set) continue;
+      const int jc = cand_cnt[base + j];
+      if (jc > cnt || (jc == cnt && (jd & 15) < root)) win = false;
+    }
+    scratch[sbase + m] = win ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s.n_cand = 0;
+  __syncthreads();
+  for (int m = threadIdx.x; m < M; m += blockDim.x)
+    if (scratch[sbase + m]) {
+      const int i = atomicAdd(&s.n_cand, 1);
+      scratch[sbase + (size_t)H * 10 + i] = m;
+    }
+  __syncthreads();
+  const int nc = s.n_cand;
+  for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+    cand[base + i] = scratch[sbase + (size_t)H * 10 + i];
+    cand_cnt[base + i] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone exact scorer for tv5_score: grid (ceil(n/1024), M), block 256
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) score_exact_list(const double* __restrict__ x1,
+                                                        const double* __restrict__ x2, int n,
+                                                        const double* __restrict__ E_list,
+                                                        double thr, int32_t* __restrict__ counts,
+                                                        uint32_t* __restrict__ masks) {
+  const int m = blockIdx.y;
+  double E[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) E[i] = E_list[9 * (size_t)m + i];
+  const int words = (n + 31) >> 5;
+  int c = 0;
+  const int k0 = blockIdx.x * 1024;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int k = k0 + r * 256 + threadIdx.x;
+    bool in = false;
+    if (k < n) {
+      const double2 p1 = reinterpret_cast<const double2*>(x1)[k];
+      const double2 p2 = reinterpret_cast<const double2*>(x2)[k];
+      in = sampson_inlier_exact(E, p1.x, p1.y, p2.x, p2.y, thr);
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0) {
+      c += __popc(bal);
+      if (masks && (k >> 5) < words) masks[(size_t)m * words + (k >> 5)] = bal;
+    }
+  }
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counts[m], c);
+}
+
+__global__ void bounds_to_lo_hi(const uint32_t* notin, const uint32_t* out, int M, int n,
+                                int32_t* lo, int32_t* hi) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) { lo[m] = n - (int)notin[m]; hi[m] = n - (int)out[m]; }
+}
+
+// ------------------------------------------------------------------------------------------
+// reference RNG index table
+// ------------------------------------------------------------------------------------------
+__global__ void ref_rng_kernel(int N, int iters, int32_t* __restrict__ sets) {
+  const int gi = threadIdx.x + blockDim.x * blockIdx.x;
+  curandState st;
+  curand_init(1234ULL, gi, 0, &st);
+  for (int it = 0; it < iters; ++it)
+    for (int i = 0; i < 5; ++i) {
+      float r = curand_uniform(&st);
+      r *= ((N - 1) - 0 + 0.999999f);
+      r += 0;
+      int idx = (int)truncf(r);
+      sets[((size_t)gi * iters + it) * 5 + i] = min(idx, N - 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FP32 peak microbenchmark: 8 independent dependent-chains per thread
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* sink, int iters, float a, float b) {
+  if (MODE == 0) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    if (s == 123.456f) sink[0] = s;
+  } else {
+    float2 v[8];
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = make_float2((float)(threadIdx.x + i), (float)i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ffma2_rn(v[i], a2, b2);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i].x + v[i].y;
+    if (s == 123.456f) sink[0] = s;
+  }
+}
+
+}  // namespace tv5
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+using namespace tv5;
+
+#define TV5_CUDA(ctx, call)                         \
+  do {                                              \
+    cudaError_t e__ = (call);                       \
+    if (e__ != cudaSuccess) {                       \
+      (ctx)->last_cuda = (int)e__;                  \
+      return TV5_ERR_CUDA;                          \
+    }                                               \
+  } while (0)
+
+template <typename T>
+static int grow(tv5_ctx* ctx, T*& p, size_t& cap, size_t need) {
+  if (need <= cap && p) return TV5_OK;
+  if (p) cudaFree(p);
+  p = nullptr;
+  size_t n = std::max(need, cap + cap / 2);
+  if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) { cap = 0; ctx->last_cuda = (int)cudaGetLastError(); return TV5_ERR_NOMEM; }
+  cap = n;
+  return TV5_OK;
+}
+template <typename T>
+static int grow_same(tv5_ctx* ctx, T*& p, size_t old_cap, size_t new_cap) {
+  if (new_cap == old_cap && p) return TV5_OK;
+  if (p) cudaFree(p);
+  p = nullptr;
+  if (cudaMalloc(&p, new_cap * sizeof(T)) != cudaSuccess) { ctx->last_cuda = (int)cudaGetLastError(); return TV5_ERR_NOMEM; }
+  return TV5_OK;
+}
+
+static int ensure_workspace(tv5_ctx* ctx, int B, size_t total_pp, size_t total_sets) {
+  Workspace& w = ctx->ws;
+  int rc;
+  if ((size_t)B > w.desc_cap || !w.desc) {
+    size_t nc = std::max((size_t)B, w.desc_cap * 2);
+    if ((rc = grow_same(ctx, w.desc, w.desc_cap, nc))) return rc;
+    if ((rc = grow_same(ctx, w.state, w.desc_cap, nc))) return rc;
+    w.desc_cap = nc;
+  }
+  if (!w.ctl && cudaMalloc(&w.ctl, sizeof(Control)) != cudaSuccess) return TV5_ERR_NOMEM;
+  if ((rc = grow(ctx, w.pp, w.pp_cap, total_pp))) return rc;
+  if (total_sets > w.sets_cap || !w.E_list) {
+    size_t nc = std::max(total_sets, w.sets_cap + w.sets_cap / 2);
+    if ((rc = grow_same(ctx, w.E_list, w.sets_cap * 90, nc * 90))) return rc;
+    if ((rc = grow_same(ctx, w.P_list, w.sets_cap * 120, nc * 120))) return rc;
+    if ((rc = grow_same(ctx, w.n_valid, w.sets_cap, nc))) return rc;
+    if ((rc = grow_same(ctx, w.n_roots, w.sets_cap, nc))) return rc;
+    if ((rc = grow_same(ctx, w.hyp, w.sets_cap * 10, nc * 10))) return rc;
+    if ((rc = grow_same(ctx, w.hyp_id, w.sets_cap * 10, nc * 10))) return rc;
+    if ((rc = grow_same(ctx, w.notin, w.sets_cap * 10, nc * 10))) return rc;
+    if ((rc = grow_same(ctx, w.out, w.sets_cap * 10, nc * 10))) return rc;
+    if ((rc = grow_same(ctx, w.cand, w.sets_cap * 30, nc * 30))) return rc;  // + 2x set_winners scratch
+    if ((rc = grow_same(ctx, w.cand_cnt, w.sets_cap * 10, nc * 10))) return rc;
+    w.sets_cap = nc;
+    w.hyp_cap = nc * 10;
+  }
+  return TV5_OK;
+}
+
+static void stage_mark(tv5_ctx* ctx, cudaStream_t st, int i) {
+  if (ctx->profiling) cudaEventRecord(ctx->ev[i], st);
+}
+
+static void profile_collect(tv5_ctx* ctx) {
+  if (!ctx->profiling || !ctx->ev_pending) return;
+  cudaEventSynchronize(ctx->ev[TV5_N_STAGES]);
+  for (int i = 0; i < TV5_N_STAGES; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) {
+      ctx->stage_ms[i] += ms;
+      ctx->stage_launches[i] += 1;
+    }
+  }
+  ctx->ev_pending = false;
+}
+
+extern "C" {
+
+int tv5_version(void) { return TV5_VERSION; }
+
+const char* tv5_strerror(int code) {
+  switch (code) {
+    case TV5_OK: return "ok";
+    case TV5_ERR_INVALID: return "invalid argument";
+    case TV5_ERR_CUDA: return "CUDA runtime error";
+    case TV5_ERR_NOMEM: return "out of device memory";
+    case TV5_ERR_NO_DEVICE: return "no usable CUDA device";
+    default: return "unknown error";
+  }
+}
+
+int tv5_create(int device, tv5_ctx** out) {
+  if (!out) return TV5_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    cudaGetLastError();
+    return TV5_ERR_NO_DEVICE;
+  }
+  tv5_ctx* ctx = new (std::nothrow) tv5_ctx();
+  if (!ctx) return TV5_ERR_NOMEM;
+  ctx->device = device;
+  int rc = TV5_OK;
+  do {
+    if (cudaSetDevice(device) != cudaSuccess) { rc = TV5_ERR_CUDA; break; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = TV5_ERR_CUDA; break; }
+    if (prop.major != 10) { rc = TV5_ERR_NO_DEVICE; break; }  // sm_100a cubin only
+    ctx->sm_count = prop.multiProcessorCount;
+    // completion rows of the null-space system: the recurrence the reference runs per call
+    // (essential_matrix_5pt.cu:639-649); plain IEEE double arithmetic, so host == device.
+    double fill[4][9];
+    double ran = 3.18730379;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 9; ++j) {
+        ran *= 3.18730379;
+        ran = 2.0 * (ran - floor(ran)) - 1.0;
+        fill[i][j] = ran;
+      }
+    if (cudaMemcpyToSymbol(c_completion, fill, sizeof(fill)) != cudaSuccess) { rc = TV5_ERR_CUDA; break; }
+    for (int i = 0; i <= TV5_N_STAGES; ++i)
+      if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { rc = TV5_ERR_CUDA; break; }
+  } while (0);
+  if (rc != TV5_OK) {
+    ctx->last_cuda = (int)cudaGetLastError();
+    delete ctx;
+    return rc;
+  }
+  *out = ctx;
+  return TV5_OK;
+}
+
+int tv5_destroy(tv5_ctx* ctx) {
+  if (!ctx) return TV5_OK;
+  cudaSetDevice(ctx->device);
+  Workspace& w = ctx->ws;
+  void* ptrs[] = {w.desc, w.state, w.ctl, w.pp, w.E_list, w.P_list, w.n_valid, w.n_roots, w.hyp,
+                  w.hyp_id, w.notin, w.out, w.cand, w.cand_cnt, w.h2d_x, w.h2d_sets, w.out_E,
+                  w.out_P, w.out_res};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (auto& t : ctx->rng_tables) cudaFree(t.sets);
+  for (int i = 0; i <= TV5_N_STAGES; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  delete ctx;
+  return TV5_OK;
+}
+
+int tv5_last_cuda_error(const tv5_ctx* ctx) { return ctx ? ctx->last_cuda : 0; }
+int tv5_device_sm_count(const tv5_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int tv5_ref_rng_sets(tv5_ctx* ctx, void* stream, int N, int iters, int32_t* sets_out) {
+  if (!ctx || N < 1 || iters < 1 || !sets_out) return TV5_ERR_INVALID;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  ref_rng_kernel<<<8, 64, 0, (cudaStream_t)stream>>>(N, iters, sets_out);
+  TV5_CUDA(ctx, cudaGetLastError());
+  return TV5_OK;
+}
+
+static int cached_rng_table(tv5_ctx* ctx, cudaStream_t st, int N, int iters, const int32_t** out) {
+  for (auto& t : ctx->rng_tables)
+    if (t.N == N && t.iters == iters) { *out = t.sets; return TV5_OK; }
+  if (ctx->rng_tables.size() >= 64) {  // bounded cache
+    // the evicted table may still be in use by work queued on another stream
+    TV5_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(ctx->rng_tables.front().sets);
+    ctx->rng_tables.erase(ctx->rng_tables.begin());
+  }
+  int32_t* p = nullptr;
+  if (cudaMalloc(&p, (size_t)TV5_REF_THREADS * iters * 5 * sizeof(int32_t)) != cudaSuccess) {
+    ctx->last_cuda = (int)cudaGetLastError();
+    return TV5_ERR_NOMEM;
+  }
+  ref_rng_kernel<<<8, 64, 0, st>>>(N, iters, p);
+  // make the table visible to work later submitted on other streams
+  TV5_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->rng_tables.push_back({N, iters, p});
+  *out = p;
+  return TV5_OK;
+}
+
+int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, const double* x2,
+                           const int64_t* pt_offsets, const int32_t* sets, int iters, int n_pre,
+                           int n_full, double thr, int with_cheirality, double* E_out,
+                           double* P_out, tv5_result* result, uint8_t* mask_out) {
+  if (!ctx || B < 1 || !x1 || !x2 || !pt_offsets || iters < 1 || !E_out || !result) return TV5_ERR_INVALID;
+  if (!(thr > 0.0) || !(thr < 1e300)) return TV5_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  profile_collect(ctx);
+  const int H = TV5_REF_THREADS * iters;
+  std::vector<PairDesc> hd((size_t)B);
+  size_t total_pp = 0;
+  int max_pp = 0, max_n = 0;
+  bool two_stage = false;
+  for (int b = 0; b < B; ++b) {
+    const int64_t n64 = pt_offsets[b + 1] - pt_offsets[b];
+    if (n64 < 1 || n64 > 0x3fffffff) return TV5_ERR_INVALID;
+    const int n = (int)n64;
+    PairDesc& d = hd[b];
+    d.x1 = x1 + 2 * pt_offsets[b];
+    d.x2 = x2 + 2 * pt_offsets[b];
+    d.n = n;
+    d.n_pre = n_pre <= 0 ? n : std::min(n_pre, n);
+    d.n_full = n_full <= 0 ? n : std::min(n_full, n);
+    if (d.n_pre != d.n_full) two_stage = true;
+    if (sets) {
+      d.sets = sets + (size_t)b * H * 5;
+    } else {
+      int rc = cached_rng_table(ctx, st, n, iters, &d.sets);
+      if (rc) return rc;
+    }
+    d.E_out = E_out + 9 * (size_t)b;
+    d.P_out = P_out ? P_out + 12 * (size_t)b : nullptr;
+    d.result = result + b;
+    d.mask_out = mask_out ? mask_out + pt_offsets[b] : nullptr;
+    d.pp_off = (int64_t)total_pp;
+    d.pad = 0;
+    const int npp = (n + 1) / 2;
+    total_pp += (size_t)npp;
+    max_pp = std::max(max_pp, npp);
+    max_n = std::max(max_n, n);
+  }
+  int rc = ensure_workspace(ctx, B, total_pp, (size_t)B * H);
+  if (rc) return rc;
+  Workspace& w = ctx->ws;
+  TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, hd.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, st));
+  TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState) * B, st));
+  const double inv_thr = 1.0 / thr;
+
+  stage_mark(ctx, st, 0);
+  prep_points<<<dim3((max_pp + 255) / 256, B), 256, 0, st>>>(w.desc, w.state, w.pp, inv_thr);
+  stage_mark(ctx, st, 1);
+  solve_sets<<<dim3((H + 63) / 64, B), 64, 0, st>>>(w.desc, w.state, H, with_cheirality, inv_thr,
+                                                   w.E_list, with_cheirality ? w.P_list : nullptr,
+                                                   w.n_valid, w.n_roots, w.hyp, w.hyp_id, w.notin,
+                                                   w.out);
+  stage_mark(ctx, st, 2);
+  // tile size: big tiles for batches, enough tiles to balance 2 CTAs/SM for a single pair
+  const int slots = 2 * ctx->sm_count;
+  int pp_per_tile = kMaxTilePairs;
+  {
+    const double est_M = (double)H * (with_cheirality ? 3.0 : 4.5);
+    const double n_hc = std::max(1.0, est_M / kHypChunk);
+    const double want_pc = 6.0 * slots / (n_hc * B);
+    if (want_pc > 1.0) {
+      int t = (int)((double)max_pp / want_pc);
+      t = (t + 7) & ~7;
+      pp_per_tile = std::max(64, std::min(kMaxTilePairs, t));
+    }
+  }
+  plan_tiles<<<1, 32, 0, st>>>(w.desc, w.state, w.ctl, B, pp_per_tile, thr, two_stage ? 0 : 1);
+  stage_mark(ctx, st, 3);
+  if (!two_stage) {
+    const int grid = slots;
+    score_bounds<<<grid, kScoreThreads, 0, st>>>(w.desc, w.state, w.ctl, B, H, pp_per_tile, w.pp,
+                                                 w.hyp, w.notin, w.out);
+  }
+  stage_mark(ctx, st, 4);
+  pick_candidates<<<B, 256, 0, st>>>(w.desc, w.state, H, w.notin, w.out, w.cand, w.cand_cnt);
+  const int X = std::max(1, std::min(4096, (4 * ctx->sm_count + B - 1) / B));
+  if (two_stage) {
+    // stage A runs on n_pre points: exact_counts reads n_full, so descriptors are swapped on
+    // the device between the two stages by re-uploading them.
+    std::vector<PairDesc> ha = hd;
+    for (auto& d : ha) d.n_full = d.n_pre;
+    TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, ha.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, st));
+    exact_counts<<<dim3(X, B), 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, w.hyp_id, w.cand, w.cand_cnt);
+    set_winners<<<B, 256, 0, st>>>(w.desc, w.state, H, w.hyp_id, w.cand, w.cand_cnt, w.cand + w.sets_cap * 10);
+    TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, hd.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, st));
+  }
+  exact_counts<<<dim3(X, B), 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, w.hyp_id, w.cand, w.cand_cnt);
+  stage_mark(ctx, st, 5);
+  finalize<<<B, 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, with_cheirality ? w.P_list : nullptr,
+                              w.hyp_id, w.cand, w.cand_cnt);
+  stage_mark(ctx, st, 6);
+  if (ctx->profiling) ctx->ev_pending = true;
+  TV5_CUDA(ctx, cudaGetLastError());
+  return TV5_OK;
+}
+
+int tv5_compute_pose(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
+                     const int32_t* sets, int iters, int n_pre, int n_full, double thr,
+                     int with_cheirality, double* E_out, double* P_out, tv5_result* result,
+                     uint8_t* mask_out) {
+  if (N < 1) return TV5_ERR_INVALID;
+  const int64_t off[2] = {0, N};
+  return tv5_compute_pose_batch(ctx, stream, 1, x1, x2, off, sets, iters, n_pre, n_full, thr,
+                                with_cheirality, E_out, P_out, result, mask_out);
+}
+
+int tv5_compute_pose_batch_host(tv5_ctx* ctx, void* stream, int B, const double* x1,
+                                const double* x2, const int64_t* pt_offsets, const int32_t* sets,
+                                int iters, int n_pre, int n_full, double thr, int with_cheirality,
+                                double* E_out, double* P_out, tv5_result* result) {
+  if (!ctx || B < 1 || !x1 || !x2 || !pt_offsets || !E_out || !result || iters < 1) return TV5_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t total = (size_t)(pt_offsets[B] - pt_offsets[0]);
+  const int H = TV5_REF_THREADS * iters;
+  Workspace& w = ctx->ws;
+  int rc;
+  if ((rc = grow(ctx, w.h2d_x, w.h2d_cap, total * 4))) return rc;
+  if (sets && (rc = grow(ctx, w.h2d_sets, w.h2d_sets_cap, (size_t)B * H * 5))) return rc;
+  if ((size_t)B > w.out_cap || !w.out_E) {
+    if ((rc = grow_same(ctx, w.out_E, w.out_cap * 9, (size_t)B * 9))) return rc;
+    if ((rc = grow_same(ctx, w.out_P, w.out_cap * 12, (size_t)B * 12))) return rc;
+    if ((rc = grow_same(ctx, w.out_res, w.out_cap, (size_t)B))) return rc;
+    w.out_cap = (size_t)B;
+  }
+  double* dx1 = w.h2d_x;
+  double* dx2 = w.h2d_x + total * 2;
+  TV5_CUDA(ctx, cudaMemcpyAsync(dx1, x1 + 2 * pt_offsets[0], total * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  TV5_CUDA(ctx, cudaMemcpyAsync(dx2, x2 + 2 * pt_offsets[0], total * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (sets)
+    TV5_CUDA(ctx, cudaMemcpyAsync(w.h2d_sets, sets, (size_t)B * H * 5 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  std::vector<int64_t> off((size_t)B + 1);
+  for (int b = 0; b <= B; ++b) off[b] = pt_offsets[b] - pt_offsets[0];
+  rc = tv5_compute_pose_batch(ctx, stream, B, dx1, dx2, off.data(), sets ? w.h2d_sets : nullptr, iters,
+                              n_pre, n_full, thr, with_cheirality, w.out_E, w.out_P, w.out_res, nullptr);
+  if (rc) return rc;
+  TV5_CUDA(ctx, cudaMemcpyAsync(E_out, w.out_E, (size_t)B * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (P_out) TV5_CUDA(ctx, cudaMemcpyAsync(P_out, w.out_P, (size_t)B * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TV5_CUDA(ctx, cudaMemcpyAsync(result, w.out_res, (size_t)B * sizeof(tv5_result), cudaMemcpyDeviceToHost, st));
+  TV5_CUDA(ctx, cudaStreamSynchronize(st));
+  return TV5_OK;
+}
+
+int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
+               const int32_t* sets, int H, int with_cheirality, double* E_list, double* P_list,
+               int32_t* n_roots, int32_t* n_valid) {
+  if (!ctx || !x1 || !x2 || N < 1 || !sets || H < 1 || !E_list || !n_valid) return TV5_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_workspace(ctx, 1, 1, 1);
+  if (rc) return rc;
+  PairDesc d;
+  memset(&d, 0, sizeof(d));
+  d.x1 = x1; d.x2 = x2; d.sets = sets; d.n = N; d.n_pre = d.n_full = N;
+  TV5_CUDA(ctx, cudaMemcpyAsync(ctx->ws.desc, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+  TV5_CUDA(ctx, cudaMemsetAsync(E_list, 0, (size_t)H * 90 * sizeof(double), st));
+  if (P_list) TV5_CUDA(ctx, cudaMemsetAsync(P_list, 0, (size_t)H * 120 * sizeof(double), st));
+  solve_sets<<<dim3((H + 63) / 64, 1), 64, 0, st>>>(ctx->ws.desc, ctx->ws.state, H, with_cheirality, 1.0,
+                                                   E_list, with_cheirality ? P_list : nullptr, n_valid,
+                                                   n_roots, nullptr, nullptr, nullptr, nullptr);
+  TV5_CUDA(ctx, cudaGetLastError());
+  return TV5_OK;
+}
+
+int tv5_score(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int n_test,
+              const double* E_list, int M, double thr, int32_t* counts, uint32_t* masks) {
+  if (!ctx || !x1 || !x2 || n_test < 0 || !E_list || M < 0 || !counts) return TV5_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (M == 0) return TV5_OK;
+  TV5_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)M * sizeof(int32_t), st));
+  if (n_test == 0) return TV5_OK;
+  for (int m0 = 0; m0 < M; m0 += 65535) {
+    const int mc = std::min(65535, M - m0);
+    score_exact_list<<<dim3((n_test + 1023) / 1024, mc), 256, 0, st>>>(
+        x1, x2, n_test, E_list + 9 * (size_t)m0, thr, counts + m0,
+        masks ? masks + (size_t)m0 * ((n_test + 31) / 32) : nullptr);
+  }
+  TV5_CUDA(ctx, cudaGetLastError());
+  return TV5_OK;
+}
+
+int tv5_score_bounds(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int n_test,
+                     const double* E_list, int M, double thr, int32_t* lo, int32_t* hi) {
+  if (!ctx || !x1 || !x2 || n_test < 1 || !E_list || M < 1 || !lo || !hi || !(thr > 0.0)) return TV5_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  profile_collect(ctx);
+  const int H = (M + 9) / 10;  // workspace is sized in sets of 10 hypotheses
+  int rc = ensure_workspace(ctx, 1, (size_t)(n_test + 1) / 2, (size_t)H);
+  if (rc) return rc;
+  Workspace& w = ctx->ws;
+  PairDesc d;
+  memset(&d, 0, sizeof(d));
+  d.x1 = x1; d.x2 = x2; d.n = n_test; d.n_pre = d.n_full = n_test; d.pp_off = 0;
+  TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+  TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState), st));
+  const double inv_thr = 1.0 / thr;
+  const int npp = (n_test + 1) / 2;
+  stage_mark(ctx, st, 0);
+  prep_points<<<dim3((npp + 255) / 256, 1), 256, 0, st>>>(w.desc, w.state, w.pp, inv_thr);
+  stage_mark(ctx, st, 1);
+  hyps_from_list<<<(M + 255) / 256, 256, 0, st>>>(E_list, M, inv_thr, w.state, w.hyp, w.hyp_id, w.notin, w.out);
+  stage_mark(ctx, st, 2);
+  const int slots = 2 * ctx->sm_count;
+  int pp_per_tile = kMaxTilePairs;
+  {
+    const double n_hc = std::max(1.0, (double)M / kHypChunk);
+    const double want_pc = 6.0 * slots / n_hc;
+    if (want_pc > 1.0) {
+      int t = (int)((double)npp / want_pc);
+      t = (t + 7) & ~7;
+      pp_per_tile = std::max(64, std::min(kMaxTilePairs, t));
+    }
+  }
+  plan_tiles<<<1, 32, 0, st>>>(w.desc, w.state, w.ctl, 1, pp_per_tile, thr, 1);
+  stage_mark(ctx, st, 3);
+  // H*10 is the stride between pairs inside the kernel; with one pair it is irrelevant
+  score_bounds<<<slots, kScoreThreads, 0, st>>>(w.desc, w.state, w.ctl, 1, H, pp_per_tile, w.pp, w.hyp,
+                                               w.notin, w.out);
+  stage_mark(ctx, st, 4);
+  bounds_to_lo_hi<<<(M + 255) / 256, 256, 0, st>>>(w.notin, w.out, M, n_test, lo, hi);
+  stage_mark(ctx, st, 5);
+  stage_mark(ctx, st, 6);
+  if (ctx->profiling) ctx->ev_pending = true;
+  TV5_CUDA(ctx, cudaGetLastError());
+  // the fast path may have been refused on the device (non-finite / huge coordinates)
+  PairState hs;
+  TV5_CUDA(ctx, cudaMemcpyAsync(&hs, w.state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  TV5_CUDA(ctx, cudaStreamSynchronize(st));
+  return hs.fast ? TV5_OK : TV5_ERR_INVALID;
+}
+
+int tv5_measure_fp32_peak(tv5_ctx* ctx, int mode, double* tflops_out) {
+  if (!ctx || !tflops_out || mode < 0 || mode > 1) return TV5_ERR_INVALID;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  float* sink = nullptr;
+  TV5_CUDA(ctx, cudaMalloc(&sink, 4));
+  const int iters = 4096, blocks = ctx->sm_count * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, 0);
+    if (mode == 0) fp32_peak_kernel<0><<<blocks, 256>>>(sink, iters, 1.0000001f, 1e-9f);
+    else fp32_peak_kernel<1><<<blocks, 256>>>(sink, iters, 1.0000001f, 1e-9f);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * 128.0 * iters * 256.0 * blocks;  // 128 FMA lanes-ops per thread per iteration
+    if (rep > 0 && ms > 0.f) best = std::max(best, flop / (ms * 1e-3) * 1e-12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  TV5_CUDA(ctx, cudaGetLastError());
+  *tflops_out = best;
+  return TV5_OK;
+}
+
+int tv5_profile_enable(tv5_ctx* ctx, int on) {
+  if (!ctx) return TV5_ERR_INVALID;
+  profile_collect(ctx);
+  ctx->profiling = on != 0;
+  return TV5_OK;
+}
+
+int tv5_profile_read(tv5_ctx* ctx, double ms_out[TV5_N_STAGES], int64_t launches_out[TV5_N_STAGES],
+                     int reset) {
+  if (!ctx) return TV5_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  profile_collect(ctx);
+  for (int i = 0; i < TV5_N_STAGES; ++i) {
+    if (ms_out) ms_out[i] = ctx->stage_ms[i];
+    if (launches_out) launches_out[i] = ctx->stage_launches[i];
+    if (reset) { ctx->stage_ms[i] = 0.0; ctx->stage_launches[i] = 0; }
+  }
+  return TV5_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// tv5_internal.h — shared declarations of the libtv5 translation units (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/tv5.h"
+#include "score.cuh"
+
+namespace tv5 {
+
+constexpr int kScoreThreads = 256;   // threads per scoring CTA
+constexpr int kHypPerThread = 2;     // hypotheses held in registers per thread
+constexpr int kHypChunk = kScoreThreads * kHypPerThread;
+constexpr int kMaxTilePairs = 512;   // point pairs staged in shared memory per tile (24 KB)
+constexpr int kExactChunk = 2048;    // points per work item of the float64 scorer
+
+// Per image pair: geometry of the job (written by the host) ...
+struct PairDesc {
+  const double* x1;       // first point of the pair, [n,2]
+  const double* x2;
+  const int32_t* sets;    // [H,5], indices local to the pair
+  double* E_out;          // [9]
+  double* P_out;          // [12] or null
+  tv5_result* result;
+  uint8_t* mask_out;      // [n_full] or null
+  int64_t pp_off;         // first PointPair32 of the pair in the workspace
+  int32_t n;              // correspondences
+  int32_t n_pre, n_full;
+  int32_t pad;
+};
+
+// ... and its device-side state (zeroed at the start of every submission).
+struct PairState {
+  int32_t M;              // hypotheses produced by the solver (atomic)
+  int32_t nonfinite;      // some coordinate is NaN/Inf
+  uint32_t r1_bits, r2_bits;  // float bits of max ||(x1,1)||^2, ||(x2,1)||^2 (atomicMax)
+  int32_t fast;           // 1: float32 guard-band scorer, 0: float64 scorer on every hypothesis
+  int32_t tile_start;     // first scoring tile of this pair
+  int32_t n_hc, n_pc;     // tiles = hypothesis chunks x point chunks
+  int32_t n_cand;         // hypotheses to re-score exactly (atomic)
+  int32_t pad;
+  BandConst band;
+};
+
+struct Control {           // one per context, zeroed per submission
+  int32_t n_tiles;
+  int32_t tile_counter;
+  int32_t pad[2];
+};
+
+struct Workspace {
+  PairDesc* desc = nullptr;  size_t desc_cap = 0;     // [B]
+  PairState* state = nullptr;                         // [B]
+  Control* ctl = nullptr;
+  PointPair32* pp = nullptr; size_t pp_cap = 0;       // [sum ceil(n/2)]
+  double* E_list = nullptr;  size_t sets_cap = 0;     // [B*H,10,9]
+  double* P_list = nullptr;                           // [B*H,10,12]
+  int32_t* n_valid = nullptr;                         // [B*H]
+  int32_t* n_roots = nullptr;                         // [B*H]
+  Hyp32* hyp = nullptr;      size_t hyp_cap = 0;      // [B*H*10]
+  int32_t* hyp_id = nullptr;                          // [B*H*10]  set*16 + root
+  uint32_t* notin = nullptr;                          // [B*H*10]
+  uint32_t* out = nullptr;                            // [B*H*10]
+  int32_t* cand = nullptr;                            // [B*H*10]  hypothesis slots to re-score
+  int32_t* cand_cnt = nullptr;                        // [B*H*10]  exact counts of the candidates
+  // staging for the host-buffer entry point
+  double* h2d_x = nullptr;   size_t h2d_cap = 0;      // [2 * sum n * 2]
+  int32_t* h2d_sets = nullptr; size_t h2d_sets_cap = 0;
+  double* out_E = nullptr;   size_t out_cap = 0;      // [B*9], [B*12], results
+  double* out_P = nullptr;
+  tv5_result* out_res = nullptr;
+};
+
+struct RngTable { int N; int iters; int32_t* sets; };
+
+}  // namespace tv5
+
+struct tv5_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int last_cuda = 0;
+  tv5::Workspace ws;
+  std::vector<tv5::RngTable> rng_tables;
+  bool profiling = false;
+  cudaEvent_t ev[TV5_N_STAGES + 1] = {};
+  double stage_ms[TV5_N_STAGES] = {};
+  int64_t stage_launches[TV5_N_STAGES] = {};
+  bool ev_pending = false;
+};

@@ -1,0 +1,296 @@
+"""Engine: one libtv5 context per CUDA device + tensor marshalling.
+
+Mirrors the argument meaning of the reference extension
+(RANSAC_FiveP/essential_matrix/essential_matrix_wrapper.cpp:45-108) and adds the batched,
+mask-returning and hypothesis-table entry points of include/tv5.h.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .lib import Tv5Error, Tv5Result
+
+REF_THREADS = 512
+
+
+def _check(ctx, rc, what):
+    if rc != 0:
+        L = _lib.load_library()
+        msg = L.tv5_strerror(rc).decode()
+        if rc == -2 and ctx is not None:
+            msg += f" (cudaError {L.tv5_last_cuda_error(ctx)})"
+        raise Tv5Error(f"{what}: {msg}")
+
+
+def _require_points(x, name):
+    # same checks and wording as CHECK_INPUT_INIT, essential_matrix_wrapper.cpp:39-42
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if x.dtype != torch.float64:
+        raise RuntimeError(f"{name} must be a double tensor")
+    if not x.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if x.dim() != 2 or x.shape[1] != 2:
+        raise RuntimeError(f"{name} must have shape [N, 2]")
+
+
+@dataclass
+class PoseResult:
+    """Outputs of one pose solve.  Tensors live on the device; `stats` is a device int32[8]
+    (tv5_result) that is only read (with a stream sync) when one of the properties is used."""
+    E: torch.Tensor
+    P: torch.Tensor
+    stats: torch.Tensor
+    mask: torch.Tensor = None
+    _host: np.ndarray = None
+
+    def _h(self):
+        if self._host is None:
+            self._host = self.stats.cpu().numpy()
+        return self._host
+
+    @property
+    def count(self):
+        return int(self._h()[..., 0]) if self.stats.dim() == 1 else self._h()[:, 0].copy()
+
+    @property
+    def best_set(self):
+        return int(self._h()[..., 1]) if self.stats.dim() == 1 else self._h()[:, 1].copy()
+
+    @property
+    def best_root(self):
+        return int(self._h()[..., 2]) if self.stats.dim() == 1 else self._h()[:, 2].copy()
+
+    @property
+    def n_hypotheses(self):
+        return int(self._h()[..., 3]) if self.stats.dim() == 1 else self._h()[:, 3].copy()
+
+    @property
+    def n_candidates(self):
+        return int(self._h()[..., 4]) if self.stats.dim() == 1 else self._h()[:, 4].copy()
+
+    @property
+    def fast_path(self):
+        return int(self._h()[..., 5]) if self.stats.dim() == 1 else self._h()[:, 5].copy()
+
+
+class Engine:
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise Tv5Error("tv5 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.L = _lib.load_library()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None
+                                   else torch.device(device).index or 0)
+        h = C.c_void_p()
+        _check(None, self.L.tv5_create(self.device.index, C.byref(h)), "tv5_create")
+        self.ctx = h
+        self.sm_count = self.L.tv5_device_sm_count(self.ctx)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.tv5_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- pose ---------------------------------------------------------------------------------
+    def compute_pose(self, x1, x2, iters, thr, n_pre=None, n_full=None, sets=None,
+                     with_cheirality=True, want_mask=False):
+        _require_points(x1, "input1")
+        _require_points(x2, "input2")
+        N = x1.shape[0]
+        if x2.shape[0] != N or N < 1:
+            raise RuntimeError("input1 and input2 must have the same, non-zero number of points")
+        n_pre = N if n_pre is None else int(n_pre)
+        n_full = N if n_full is None else int(n_full)
+        with torch.cuda.device(self.device):
+            E = torch.empty(3, 3, dtype=torch.float64, device=self.device)
+            P = torch.empty(3, 4, dtype=torch.float64, device=self.device)
+            stats = torch.empty(8, dtype=torch.int32, device=self.device)
+            mask = torch.empty(min(n_full, N), dtype=torch.uint8, device=self.device) if want_mask else None
+            sp = None
+            if sets is not None:
+                sets = self._sets(sets, iters)
+                sp = sets.data_ptr()
+            rc = self.L.tv5_compute_pose(self.ctx, self._stream(), x1.data_ptr(), x2.data_ptr(), N,
+                                         sp, int(iters), n_pre, n_full, float(thr),
+                                         int(bool(with_cheirality)), E.data_ptr(), P.data_ptr(),
+                                         stats.data_ptr(), mask.data_ptr() if want_mask else None)
+        _check(self.ctx, rc, "tv5_compute_pose")
+        return PoseResult(E, P, stats, mask)
+
+    def _sets(self, sets, iters, B=1):
+        if not isinstance(sets, torch.Tensor):
+            sets = torch.as_tensor(np.ascontiguousarray(sets, dtype=np.int32))
+        sets = sets.to(device=self.device, dtype=torch.int32).contiguous()
+        if sets.numel() != B * REF_THREADS * int(iters) * 5:
+            raise RuntimeError(f"sets must hold {B}x{REF_THREADS * int(iters)}x5 indices")
+        return sets
+
+    def compute_pose_batch(self, x1, x2, offsets, iters, thr, n_pre=0, n_full=0, sets=None,
+                           with_cheirality=True, want_mask=False):
+        """x1, x2: [sum N_b, 2] float64 CUDA; offsets: [B+1] prefix sums (host ints)."""
+        _require_points(x1, "input1")
+        _require_points(x2, "input2")
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        B = off.size - 1
+        if B < 1 or off[0] != 0 or off[-1] != x1.shape[0] or x2.shape[0] != x1.shape[0]:
+            raise RuntimeError("offsets must be prefix sums covering all points")
+        with torch.cuda.device(self.device):
+            E = torch.empty(B, 3, 3, dtype=torch.float64, device=self.device)
+            P = torch.empty(B, 3, 4, dtype=torch.float64, device=self.device)
+            stats = torch.empty(B, 8, dtype=torch.int32, device=self.device)
+            mask = torch.empty(x1.shape[0], dtype=torch.uint8, device=self.device) if want_mask else None
+            sp = None
+            if sets is not None:
+                sets = self._sets(sets, iters, B)
+                sp = sets.data_ptr()
+            rc = self.L.tv5_compute_pose_batch(
+                self.ctx, self._stream(), B, x1.data_ptr(), x2.data_ptr(),
+                off.ctypes.data_as(C.POINTER(C.c_int64)), sp, int(iters), int(n_pre), int(n_full),
+                float(thr), int(bool(with_cheirality)), E.data_ptr(), P.data_ptr(), stats.data_ptr(),
+                mask.data_ptr() if want_mask else None)
+        _check(self.ctx, rc, "tv5_compute_pose_batch")
+        return PoseResult(E, P, stats, mask)
+
+    def compute_pose_batch_host(self, x1, x2, offsets, iters, thr, n_pre=0, n_full=0, sets=None,
+                                with_cheirality=True):
+        """Host numpy buffers in, host numpy out (copies inside); synchronous."""
+        x1 = np.ascontiguousarray(x1, dtype=np.float64)
+        x2 = np.ascontiguousarray(x2, dtype=np.float64)
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        B = off.size - 1
+        E = np.empty((B, 3, 3))
+        P = np.empty((B, 3, 4))
+        res = (Tv5Result * B)()
+        sp = None
+        if sets is not None:
+            sets = np.ascontiguousarray(sets, dtype=np.int32)
+            sp = sets.ctypes.data
+        with torch.cuda.device(self.device):
+            rc = self.L.tv5_compute_pose_batch_host(
+                self.ctx, self._stream(), B, x1.ctypes.data, x2.ctypes.data,
+                off.ctypes.data_as(C.POINTER(C.c_int64)), sp, int(iters), int(n_pre), int(n_full),
+                float(thr), int(bool(with_cheirality)), E.ctypes.data, P.ctypes.data,
+                C.cast(res, C.c_void_p))
+        _check(self.ctx, rc, "tv5_compute_pose_batch_host")
+        stats = np.frombuffer(res, dtype=np.int32).reshape(B, 8).copy()
+        return E, P, stats
+
+    # -- building blocks ----------------------------------------------------------------------
+    def solve5(self, x1, x2, sets, with_cheirality=True):
+        _require_points(x1, "input1")
+        _require_points(x2, "input2")
+        if not isinstance(sets, torch.Tensor):
+            sets = torch.as_tensor(np.ascontiguousarray(sets, dtype=np.int32))
+        sets = sets.to(device=self.device, dtype=torch.int32).contiguous().view(-1, 5)
+        H = sets.shape[0]
+        with torch.cuda.device(self.device):
+            E = torch.empty(H, 10, 3, 3, dtype=torch.float64, device=self.device)
+            P = torch.empty(H, 10, 3, 4, dtype=torch.float64, device=self.device)
+            nr = torch.empty(H, dtype=torch.int32, device=self.device)
+            nv = torch.empty(H, dtype=torch.int32, device=self.device)
+            rc = self.L.tv5_solve5(self.ctx, self._stream(), x1.data_ptr(), x2.data_ptr(),
+                                   x1.shape[0], sets.data_ptr(), H, int(bool(with_cheirality)),
+                                   E.data_ptr(), P.data_ptr(), nr.data_ptr(), nv.data_ptr())
+        _check(self.ctx, rc, "tv5_solve5")
+        return dict(E=E, P=P, n_roots=nr, n_valid=nv)
+
+    def score(self, x1, x2, E_list, thr, n_test=None, want_mask=False):
+        _require_points(x1, "input1")
+        _require_points(x2, "input2")
+        E_list = E_list.to(device=self.device, dtype=torch.float64).contiguous().view(-1, 9)
+        M = E_list.shape[0]
+        n = x1.shape[0] if n_test is None else int(n_test)
+        with torch.cuda.device(self.device):
+            counts = torch.empty(M, dtype=torch.int32, device=self.device)
+            masks = torch.zeros(M, (n + 31) // 32, dtype=torch.int32, device=self.device) if want_mask else None
+            rc = self.L.tv5_score(self.ctx, self._stream(), x1.data_ptr(), x2.data_ptr(), n,
+                                  E_list.data_ptr(), M, float(thr), counts.data_ptr(),
+                                  masks.data_ptr() if want_mask else None)
+        _check(self.ctx, rc, "tv5_score")
+        return (counts, masks) if want_mask else counts
+
+    def score_bounds(self, x1, x2, E_list, thr, n_test=None):
+        _require_points(x1, "input1")
+        _require_points(x2, "input2")
+        E_list = E_list.to(device=self.device, dtype=torch.float64).contiguous().view(-1, 9)
+        M = E_list.shape[0]
+        n = x1.shape[0] if n_test is None else int(n_test)
+        with torch.cuda.device(self.device):
+            lo = torch.empty(M, dtype=torch.int32, device=self.device)
+            hi = torch.empty(M, dtype=torch.int32, device=self.device)
+            rc = self.L.tv5_score_bounds(self.ctx, self._stream(), x1.data_ptr(), x2.data_ptr(), n,
+                                         E_list.data_ptr(), M, float(thr), lo.data_ptr(), hi.data_ptr())
+        _check(self.ctx, rc, "tv5_score_bounds")
+        return lo, hi
+
+    def ref_rng_sets(self, N, iters):
+        with torch.cuda.device(self.device):
+            out = torch.empty(REF_THREADS * int(iters), 5, dtype=torch.int32, device=self.device)
+            rc = self.L.tv5_ref_rng_sets(self.ctx, self._stream(), int(N), int(iters), out.data_ptr())
+        _check(self.ctx, rc, "tv5_ref_rng_sets")
+        return out
+
+    # -- measurement --------------------------------------------------------------------------
+    def measure_fp32_peak(self, mode=1):
+        v = C.c_double()
+        with torch.cuda.device(self.device):
+            _check(self.ctx, self.L.tv5_measure_fp32_peak(self.ctx, int(mode), C.byref(v)), "fp32 peak")
+        return v.value
+
+    def profile_enable(self, on=True):
+        _check(self.ctx, self.L.tv5_profile_enable(self.ctx, int(bool(on))), "profile_enable")
+
+    def profile_read(self, reset=True):
+        ms = (C.c_double * _lib.TV5_N_STAGES)()
+        n = (C.c_int64 * _lib.TV5_N_STAGES)()
+        _check(self.ctx, self.L.tv5_profile_read(self.ctx, ms, n, int(bool(reset))), "profile_read")
+        return {name: (ms[i], n[i]) for i, name in enumerate(_lib.STAGE_NAMES)}
+
+
+_engines = {}
+
+
+def get_engine(device=None):
+    """Cached Engine of a device (default: current CUDA device)."""
+    if not torch.cuda.is_available():
+        raise Tv5Error("tv5 needs a CUDA device (sm_100a); there is no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    if idx not in _engines:
+        _engines[idx] = Engine(torch.device("cuda", idx))
+    return _engines[idx]
+
+
+def compute_pose(x1, x2, iters, thr, **kw):
+    return get_engine(x1.device).compute_pose(x1, x2, iters, thr, **kw)
+
+
+def compute_pose_batch(x1, x2, offsets, iters, thr, **kw):
+    return get_engine(x1.device).compute_pose_batch(x1, x2, offsets, iters, thr, **kw)
+
+
+def solve5(x1, x2, sets, **kw):
+    return get_engine(x1.device).solve5(x1, x2, sets, **kw)
+
+
+def score(x1, x2, E_list, thr, **kw):
+    return get_engine(x1.device).score(x1, x2, E_list, thr, **kw)
+
+
+def score_bounds(x1, x2, E_list, thr, **kw):
+    return get_engine(x1.device).score_bounds(x1, x2, E_list, thr, **kw)
+
+
+def ref_rng_sets(N, iters, device=None):
+    return get_engine(device).ref_rng_sets(N, iters)

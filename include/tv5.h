@@ -1,0 +1,182 @@
+/*
+ * tv5.h — C ABI of libtv5: a B200 (sm_100a) two-view relative-pose engine.
+ *
+ * This is the drop-in boundary for the geometric core of Deep-SfM-Revisited's SFMnet.  Every
+ * entry point names the reference interface it replaces (paths relative to
+ * /root/reference/RANSAC_FiveP/essential_matrix/).  Plain pointers and sizes only; no torch
+ * types.  All pointers marked "device" are CUDA device pointers on the context's device; all
+ * work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream)
+ * and is asynchronous unless stated otherwise.  Functions return 0 on success or a negative
+ * tv5 error code (tv5_strerror); they never print and never call exit() — unlike the
+ * reference's CudaErrorCheck (essential_matrix.cu:17-24).
+ *
+ * Conventions (identical to the reference):
+ *   x1, x2     [N,2] row-major float64, K^-1-normalised image coordinates; x2^T E x1 = 0
+ *   E          3x3 row-major, unnormalised (||E||_F = sqrt(w^2+x^2+y^2+1)), arbitrary sign
+ *   P          3x4 row-major [R | t], X2 = R X1 + t, ||t|| = 1, chosen by the unanimous
+ *              cheirality vote of the 5 sample points (cheirality.cu:4-214)
+ *   inlier     iff Sampson distance |x2'Ex1| / sqrt((Ex1)_0^2+(Ex1)_1^2+(E'x2)_0^2+(E'x2)_1^2)
+ *              <= thr in float64, evaluated with the reference's exact operation order
+ *              (kernel_functions.cu:231-264) — decisions are bit-identical to the reference.
+ *   sets       [H,5] int32 minimal-set index table, hypothesis id h = thread*iters + it
+ *              (thread in [0,512)), which reproduces the reference's tie-break order
+ *              "first maximum over (thread, iteration, root)" (kernel_functions.cu:198,215;
+ *              essential_matrix.cu:252).
+ */
+#ifndef TV5_H_
+#define TV5_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TV5_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define TV5_OK 0
+#define TV5_ERR_INVALID (-1)   /* bad argument */
+#define TV5_ERR_CUDA (-2)      /* CUDA runtime error (see tv5_last_cuda_error) */
+#define TV5_ERR_NOMEM (-3)     /* workspace allocation failed */
+#define TV5_ERR_NO_DEVICE (-4) /* no sm_100 device / device index out of range */
+
+#define TV5_REF_THREADS 512 /* the reference's fixed 8 x 64 launch, essential_matrix.cu:201-203 */
+#define TV5_MAX_SOLUTIONS 10
+
+typedef struct tv5_ctx tv5_ctx;
+
+/* Per-device context: owns the workspace (grown on demand, never shrunk) and the cached
+ * reference-RNG index tables.  No global state — replaces the reference's module-level
+ * __constant__ parameters (kernel_functions.cu:16-20) and its per-call cudaMallocManaged /
+ * cudaFree (essential_matrix.cu:222-274).  A context may be used from one host thread at a
+ * time; different contexts are independent. */
+int tv5_create(int device, tv5_ctx** out);
+int tv5_destroy(tv5_ctx* ctx);
+const char* tv5_strerror(int code);
+int tv5_last_cuda_error(const tv5_ctx* ctx); /* cudaError_t of the last TV5_ERR_CUDA */
+int tv5_version(void);
+int tv5_device_sm_count(const tv5_ctx* ctx);
+
+/* Result record written by the pose entry points (device, 8 x int32 per pair). */
+typedef struct tv5_result {
+  int32_t count;        /* inliers of the winner on the first n_full points (0 if none) */
+  int32_t best_set;     /* winning hypothesis id h in [0,H), -1 if no hypothesis scored > 0 */
+  int32_t best_root;    /* index of the winner inside its set's (cheirality-compacted) list */
+  int32_t n_hypotheses; /* sum over sets of the number of scored solutions (M) */
+  int32_t n_candidates; /* hypotheses re-scored exactly in float64 by the guard-band pass */
+  int32_t fast_path;    /* 1 = float32 guard-band scorer used, 0 = all-float64 scorer */
+  int32_t reserved[2];
+} tv5_result;
+
+/*
+ * tv5_compute_pose — replaces ProjectionMatrixRansac (essential_matrix.cu:190-280, Python
+ * `essential_matrix.computeP`) when with_cheirality != 0 and EssentialMatrixInitialise
+ * (essential_matrix.cu:110-184, `essential_matrix.initialise`) when with_cheirality == 0.
+ *
+ *   x1, x2        device [N,2] float64
+ *   sets          device [H,5] int32, H = TV5_REF_THREADS * iters; NULL => the table the
+ *                 reference would draw (curand XORWOW, seed 1234, kernel_functions.cu:45-48,
+ *                 269-300), generated on the device and cached per (N, iters)
+ *   iters         num_ransac_iterations (minimal sets per reference thread)
+ *   n_pre         num_test_points: points used to pick the best root inside a set
+ *   n_full        num_ransac_test_points: points used to rank sets
+ *   thr           inlier threshold on the unsquared Sampson distance
+ *   E_out         device [9] float64
+ *   P_out         device [12] float64 (zeros when with_cheirality == 0); may be NULL
+ *   result        device tv5_result
+ *   mask_out      device [n_full] uint8 inlier mask of the winner, or NULL  (extension: the
+ *                 reference returns no mask)
+ * Defined divergences from the reference's undefined behaviour: sets with
+ * no surviving solution score nothing; indices are clamped to N-1; if no hypothesis has a
+ * non-zero count E and P are zero and best_set = -1.
+ */
+int tv5_compute_pose(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
+                     const int32_t* sets, int iters, int n_pre, int n_full, double thr,
+                     int with_cheirality, double* E_out, double* P_out, tv5_result* result,
+                     uint8_t* mask_out);
+
+/*
+ * tv5_compute_pose_batch — B independent pairs in one stream-ordered submission (the
+ * reference loops over pairs in Python, models/SFMnet.py:229-272).
+ *   x1, x2        device [sum N_b, 2] float64, pairs concatenated
+ *   pt_offsets    HOST [B+1] int64 prefix sums of N_b
+ *   sets          device [B,H,5] int32 with indices local to each pair, or NULL (reference RNG
+ *                 table per pair; all pairs with the same N share one table, as B successive
+ *                 reference calls would)
+ *   n_pre/n_full  <= 0 means "all N_b points of the pair" (what SFMnet passes)
+ *   E_out [B,9], P_out [B,12] (or NULL), result [B], mask_out [sum N_b] or NULL: device
+ */
+int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, const double* x2,
+                           const int64_t* pt_offsets, const int32_t* sets, int iters, int n_pre,
+                           int n_full, double thr, int with_cheirality, double* E_out,
+                           double* P_out, tv5_result* result, uint8_t* mask_out);
+
+/*
+ * Host-buffer convenience used by non-torch callers and by bench.py's end-to-end leg: copies
+ * x1/x2 (and sets, if given) from HOST memory, runs tv5_compute_pose_batch, copies E, P and
+ * result back and synchronises the stream.  All pointers are HOST pointers.
+ */
+int tv5_compute_pose_batch_host(tv5_ctx* ctx, void* stream, int B, const double* x1,
+                                const double* x2, const int64_t* pt_offsets, const int32_t* sets,
+                                int iters, int n_pre, int n_full, double thr, int with_cheirality,
+                                double* E_out, double* P_out, tv5_result* result);
+
+/*
+ * tv5_solve5 — five-point solver + cheirality for H minimal sets; replaces
+ * compute_E_matrices_optimized (essential_matrix_5pt.cu:1224-1249) followed by
+ * compute_P_matrices (cheirality.cu:4-214) as called at kernel_functions.cu:163,180.
+ *   E_list  device [H,10,9]  solutions in ascending order of the hidden variable w; when
+ *                            with_cheirality != 0 the list is compacted to the valid ones
+ *   P_list  device [H,10,12] or NULL
+ *   n_roots device [H] or NULL (number of real roots)
+ *   n_valid device [H]       (number of entries in E_list / P_list)
+ */
+int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
+               const int32_t* sets, int H, int with_cheirality, double* E_list, double* P_list,
+               int32_t* n_roots, int32_t* n_valid);
+
+/*
+ * tv5_score — exact float64 Sampson inlier counts of M essential matrices on the first n_test
+ * points; replaces the scoring loops + ComputeError<double> (kernel_functions.cu:184-214,
+ * 231-264).  counts device [M] int32; masks device [M, ceil(n_test/32)] uint32 bit-packed
+ * (bit k%32 of word k/32 = point k is an inlier) or NULL.
+ */
+int tv5_score(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int n_test,
+              const double* E_list, int M, double thr, int32_t* counts, uint32_t* masks);
+
+/*
+ * tv5_score_bounds — the float32 guard-band scorer used by the fast path, exposed for tests
+ * and roofline measurement: lo[m] <= exact count[m] <= hi[m] for every m (lo counts the
+ * evaluations that are inliers under every rounding, hi adds the undecidable ones).
+ * lo, hi device [M] int32.  Returns TV5_ERR_INVALID if the coordinates are not finite or too
+ * large for the float32 bound (the pose entry points then use the float64 scorer).
+ */
+int tv5_score_bounds(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int n_test,
+                     const double* E_list, int M, double thr, int32_t* lo, int32_t* hi);
+
+/*
+ * tv5_ref_rng_sets — the index table the reference draws for (N, iters): 512 curand XORWOW
+ * states curand_init(1234, tid, 0), 5 x curand_uniform per set, index =
+ * trunc(u * (N - 1 + 0.999999f)) in float32 (kernel_functions.cu:45-48, 269-300), clamped to
+ * N-1.  sets_out device [512*iters, 5] int32.
+ */
+int tv5_ref_rng_sets(tv5_ctx* ctx, void* stream, int N, int iters, int32_t* sets_out);
+
+/* Device-timed (CUDA events) measurements used by bench.py; both synchronise. */
+
+/* FP32 FMA-chain peak of this GPU in TFLOP/s: mode 0 = scalar FFMA, 1 = packed FFMA2. */
+int tv5_measure_fp32_peak(tv5_ctx* ctx, int mode, double* tflops_out);
+
+/* Average duration in milliseconds of each pipeline stage over the launches since the last
+ * reset (CUDA events recorded on the launching stream when profiling is enabled).
+ * stage ids: 0 prep, 1 solve, 2 plan, 3 score_bounds, 4 candidates+exact, 5 finalize. */
+#define TV5_N_STAGES 6
+int tv5_profile_enable(tv5_ctx* ctx, int on);
+int tv5_profile_read(tv5_ctx* ctx, double ms_out[TV5_N_STAGES], int64_t launches_out[TV5_N_STAGES],
+                     int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TV5_H_ */

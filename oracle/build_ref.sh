@@ -1,10 +1,9 @@
 #!/usr/bin/env bash
 # TEST INFRASTRUCTURE.  Builds compiled copies of the *reference* into oracle/_ref/ (git-ignored,
 # NOT gpurun-ignored, so the .so files travel to the GPU box).  Nothing under /root/reference is
-# copied into the repo: sources are compiled where they lie (the stock extension is built from a
-# scratch copy under /tmp because setuptools writes into the source tree).
+# copied into the repo: sources are compiled where they lie, objects go to a scratch dir in /tmp.
 #
-#   oracle/_ref/refext/essential_matrix*.so  unmodified reference extension (TORCH_CUDA_ARCH_LIST=10.0a)
+#   oracle/_ref/refext/essential_matrix*.so  unmodified reference extension, compiled directly with nvcc/g++
 #   oracle/_ref/libref_twin_cuda.so          instrumented twin, nvcc, sm_100a (GPU box only)
 #   oracle/_ref/libref_host.so               reference solver+cheirality host-compiled with g++
 #
@@ -31,10 +30,23 @@ build_twin() {
   echo "built $OUT/libref_twin_cuda.so"
 }
 build_ext() {
-  local tmp; tmp="$(mktemp -d /tmp/ref_ext_build.XXXXXX)"
-  cp -r "$REF" "$tmp/RANSAC_FiveP"
-  ( cd "$tmp/RANSAC_FiveP" && TORCH_CUDA_ARCH_LIST=10.0a MAX_JOBS=2 \
-      python setup.py -q build_ext --build-lib "$OUT/refext" --build-temp "$tmp/build" )
+  # Direct compile of the reference's two translation units (no setup.py): same defines and
+  # arch flag torch.utils.cpp_extension would pass, system g++, CUDA runtime linked statically.
+  local py_inc torch_dir ext_suffix tmp
+  py_inc="$(python -c 'import sysconfig; print(sysconfig.get_paths()["include"])')"
+  torch_dir="$(python -c 'import torch, os; print(os.path.dirname(torch.__file__))')"
+  ext_suffix="$(python -c 'import sysconfig; print(sysconfig.get_config_var("EXT_SUFFIX"))')"
+  tmp="$(mktemp -d /tmp/ref_ext_build.XXXXXX)"
+  mkdir -p "$OUT/refext"
+  local defs="-D__CUDA_NO_HALF_OPERATORS__ -D__CUDA_NO_HALF_CONVERSIONS__ -D__CUDA_NO_BFLOAT16_CONVERSIONS__ -D__CUDA_NO_HALF2_OPERATORS__ -DTORCH_API_INCLUDE_EXTENSION_H -DTORCH_EXTENSION_NAME=essential_matrix"
+  local incs="-I$torch_dir/include -I$torch_dir/include/torch/csrc/api/include -I/usr/local/cuda/include -I$py_inc"
+  /usr/bin/g++ -O2 -fPIC -std=c++17 -w $defs $incs -c "$REF/essential_matrix/essential_matrix_wrapper.cpp" -o "$tmp/wrapper.o" &
+  nvcc -ccbin /usr/bin/g++ -std=c++17 -w --expt-relaxed-constexpr -Xcompiler -fPIC $defs $incs \
+       -gencode=arch=compute_100a,code=sm_100a -c "$REF/essential_matrix/essential_matrix.cu" -o "$tmp/em.o"
+  wait
+  nvcc -ccbin /usr/bin/g++ -shared -cudart static "$tmp/wrapper.o" "$tmp/em.o" \
+       -L"$torch_dir/lib" -lc10 -ltorch -ltorch_cpu -ltorch_python -lc10_cuda -ltorch_cuda \
+       -o "$OUT/refext/essential_matrix$ext_suffix"
   rm -rf "$tmp"
   echo "built $(ls "$OUT"/refext/essential_matrix*.so)"
 }
