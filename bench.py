@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py — two-view E+pose solves/s @ 10k correspondences x 4096 hypotheses (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the whole hot path (prep -> 5-pt solve -> Sampson scoring -> selection ->
+pose) over one batch of PAIRS_PER_GPU synthetic KITTI-shaped pairs per GPU (config 2's shape per
+pair; the batch is config 3's).  Pairs are independent, so ranks shard by pair with no data-path
+collective ("scaling": "weak"); for N > 1 the only NCCL call is the final all_gather of the
+176-byte results.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "deep-sfm-revisited_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+N_CORR = 10000
+ITERS = 8                 # 512 reference threads x 8 iterations = 4096 hypotheses
+H = 512 * ITERS
+THR = 1e-4
+PAIRS_PER_GPU = 256
+FLOP_PER_EVAL = 34        # 15 FMA + 3 MUL + 1 compare
+KERNELS_PER_STEP = 7      # prep, solve, plan, score_bounds, pick_candidates, exact_counts, finalize
+METRIC = "two-view E+pose pair-solves/s @10k corr x 4096 hyp"
+UNIT = "pairs/s"
+
+
+def config(pairs_per_step, parallelism):
+    return {"workload": "configs[1] shape per pair (synthetic KITTI 370x1226 pair, 10,000 float64 correspondences, "
+                        "4,096 five-point hypotheses, thr 1e-4, all points scored); "
+                        f"{pairs_per_step} independent pairs per step per GPU (configs[2] batch)",
+            "pairs_per_step_per_gpu": pairs_per_step, "n_corr": N_CORR, "n_hyp": H, "thr": THR,
+            "parallelism": parallelism,
+            "l2": "inputs + workspace touched per step (~2.6 GB for 256 pairs) exceed the 126 MB L2; no flush needed"}
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(first_pair, n_pairs):
+    from tv5 import synth
+    pairs = [synth.make_pair(N_CORR, **synth.pair_variation(first_pair + i)) for i in range(n_pairs)]
+    x1 = np.concatenate([p["x1"] for p in pairs])
+    x2 = np.concatenate([p["x2"] for p in pairs])
+    sets = np.stack([synth.make_sets(N_CORR, H, 7000 + first_pair + i) for i in range(n_pairs)])
+    return pairs, x1, x2, sets
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the host-compiled reference solver + the oracle's scorer on a bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_baseline(sample_sets=H):
+    import oracle
+    from tv5 import synth
+    sc = synth.make_pair(N_CORR, 1234)
+    sets = synth.make_sets(N_CORR, H, 5)[:sample_sets]
+    kind = "port"
+    t0 = time.perf_counter()
+    if oracle.ref_host_available():
+        kind = "reference solver (oracle/_ref/libref_host.so) + port scorer"
+        d = oracle.ref_solve_sets(sc["x1"], sc["x2"], sets)
+        E, nv = d["E"], d["n_valid"]
+    else:
+        d = oracle.solve_sets(sc["x1"], sc["x2"], sets, True)
+        E, nv = d["E"], d["n_valid"]
+    t_solve = time.perf_counter() - t0
+    El = np.concatenate([E[h, :nv[h]] for h in range(len(sets))]).reshape(-1, 9)
+    t0 = time.perf_counter()
+    oracle.score(sc["x1"], sc["x2"], El, THR)
+    t_score = time.perf_counter() - t0
+    # the reference additionally re-scores each set's best root: (c+1)/c more evals
+    t_pair = (t_solve + t_score * (1.0 + len(sets) / max(len(El), 1))) * (H / len(sets))
+    out = {"value": 1.0 / t_pair, "unit": UNIT, "cores": 1, "kind": kind,
+           "sample": f"{len(sets)} of the {H} minimal sets of one pair ({len(El)} hypotheses x {N_CORR} points, "
+                     f"{t_solve + t_score:.1f} s), scaled to a full pair"}
+    try:
+        import cv2
+        x1 = sc["x1"]; x2 = sc["x2"]
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            Ecv, mask = cv2.findEssentialMat(x1, x2, np.eye(3), cv2.RANSAC, 0.999999, THR, 4096)
+            if Ecv is not None and Ecv.shape[0] >= 3:
+                cv2.recoverPose(Ecv[:3], x1, x2, np.eye(3), mask=mask)
+            ts.append(time.perf_counter() - t0)
+        out["cv2_findEssentialMat_recoverPose_pairs_per_s"] = 1.0 / float(np.median(ts))
+        out["cv2_threads"] = cv2.getNumThreads()
+        out["host_cpus"] = os.cpu_count()
+    except Exception as e:  # OpenCV missing: baseline simply not reported
+        out["cv2_error"] = str(e)[:80]
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------------------
+REF_WORKER = r'''
+import ctypes as C, importlib.util, json, os, sys, time
+import numpy as np, torch
+root, mode, steps, warmup, pairs_per_step = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+sys.path.insert(0, os.path.join(root, "deep-sfm-revisited_b200"))
+from tv5 import synth
+N, iters, thr = 10000, 8, 1e-4
+pairs = [synth.make_pair(N, **synth.pair_variation(i)) for i in range(pairs_per_step)]
+xs = [(torch.from_numpy(p["x1"]).cuda(), torch.from_numpy(p["x2"]).cuda()) for p in pairs]
+if mode == "ext":
+    d = os.path.join(root, "oracle", "_ref", "refext")
+    so = [f for f in os.listdir(d) if f.endswith(".so")][0]
+    spec = importlib.util.spec_from_file_location("essential_matrix", os.path.join(d, so))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    def solve(a, b):
+        E, P, c = m.computeP(a, b, N, N, iters, thr)
+        return int(c)
+else:
+    T = C.CDLL(os.path.join(root, "oracle", "_ref", "libref_twin_cuda.so"))
+    vp = C.c_void_p
+    T.ref_compute_pose.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp, C.POINTER(C.c_int32), C.c_int]
+    E = torch.empty(9, dtype=torch.float64, device="cuda"); P = torch.empty(12, dtype=torch.float64, device="cuda")
+    managed = 1 if mode == "twin_managed" else 0
+    def solve(a, b):
+        c = C.c_int32()
+        rc = T.ref_compute_pose(a.data_ptr(), b.data_ptr(), N, N, N, iters, thr, E.data_ptr(), P.data_ptr(), C.byref(c), managed)
+        if rc: raise RuntimeError(f"cuda error {rc}")
+        return c.value
+counts = []
+def step():
+    for a, b in xs:
+        counts.append(solve(a, b))
+for _ in range(warmup): step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter(); e0.record()
+for _ in range(steps): step()
+e1.record(); torch.cuda.synchronize()
+wall = time.perf_counter() - t0
+print("RESULT " + json.dumps(dict(ms_per_step=e0.elapsed_time(e1) / steps, wall_ms_per_step=1e3 * wall / steps, counts=counts[:4])))
+'''
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pairs_per_step = 2
+    line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config(pairs_per_step, "single GPU, one pair per call (rank 0 only)")}
+    tried = []
+    for mode, what in (("ext", "unmodified reference extension (oracle/_ref/refext), essential_matrix.computeP per pair"),
+                       ("twin_managed", "reference kernels SetupRandomState + EstimateProjectionMatrix<5> driven by the host "
+                                        "flow of essential_matrix.cu:190-280 restated in oracle/ref_twin (managed memory)"),
+                       ("twin", "same, with cudaMalloc instead of cudaMallocManaged")):
+        try:
+            pr = subprocess.run([sys.executable, "-c", REF_WORKER, ROOT, mode, str(args.steps), str(args.warmup), str(pairs_per_step)],
+                                capture_output=True, text=True, timeout=1500)
+        except subprocess.TimeoutExpired:
+            tried.append(f"{mode}: timeout")
+            continue
+        res = [l for l in pr.stdout.splitlines() if l.startswith("RESULT ")]
+        if pr.returncode == 0 and res:
+            r = json.loads(res[-1][7:])
+            v = pairs_per_step / (r["ms_per_step"] * 1e-3)
+            line.update({"value": v, "ms_per_step": r["ms_per_step"], "reference_kind": what,
+                         "reference_counts": r["counts"], "reference_attempts": tried,
+                         "e2e": {"value": pairs_per_step / (r["wall_ms_per_step"] * 1e-3), "unit": UNIT,
+                                 "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                         "gpu_launches": 2 * pairs_per_step * args.steps})
+            cb = cpu_baseline()
+            line["cpu_baseline"] = cb
+            print(json.dumps(line), flush=True)
+            return
+        msg = (pr.stdout + pr.stderr).strip().splitlines()
+        tried.append(f"{mode}: rc {pr.returncode} {msg[-1][:160] if msg else ''}")
+    # no GPU form of the reference ran: time its CPU form (bounded sample), all in this process
+    cb = cpu_baseline()
+    line.update({"value": cb["value"], "ms_per_step": 1e3 / cb["value"], "reference_kind": "CPU: " + cb["kind"],
+                 "reference_attempts": tried, "cpu_baseline": cb,
+                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import tv5
+    from tv5 import dist as tdist
+    from tv5 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = tv5.get_engine(dev)
+    B = args.pairs
+    pairs, x1h, x2h, setsh = make_batch(rank * B, B)
+    off = np.arange(B + 1, dtype=np.int64) * N_CORR
+    x1 = torch.from_numpy(x1h).to(dev)
+    x2 = torch.from_numpy(x2h).to(dev)
+    sets = torch.from_numpy(setsh).to(dev)
+    n_total = B * world
+
+    def step():
+        r = eng.compute_pose_batch(x1, x2, off, ITERS, THR, sets=sets)
+        if world > 1:   # final gather of the 176-byte results
+            return tdist.gather_pair_results(r.E, r.P, r.stats, n_total)
+        return r.E, r.P, r.stats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = float(ms.item()) / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # end to end through the C ABI with HOST buffers (pinned): H2D of x1, x2, sets and D2H of
+    # E, P, result inside the timed region, every step
+    px1 = torch.from_numpy(x1h).pin_memory()
+    px2 = torch.from_numpy(x2h).pin_memory()
+    pst = torch.from_numpy(setsh).pin_memory()
+    def e2e_step():
+        return eng.compute_pose_batch_host(px1.numpy(), px2.numpy(), off, ITERS, THR, sets=pst.numpy())
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    n_e2e = max(3, args.steps // 2)
+    for _ in range(n_e2e):
+        Eh, Ph, sth = e2e_step()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = n_total / (float(ms2.item()) / n_e2e * 1e-3)
+    h2d = int(px1.numel() * 8 + px2.numel() * 8 + pst.numel() * 4)
+    d2h = int(B * (72 + 96 + 32))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- everything below: rank 0 only, outside the timed regions -------------------------
+    Eo, Po, so = out
+    so_h = so.cpu().numpy()
+    M_total = float(so_h[:B, 3].sum())
+    evals = M_total * N_CORR
+    eng.profile_enable(True)
+    for _ in range(5):
+        eng.compute_pose_batch(x1, x2, off, ITERS, THR, sets=sets)
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    stage_ms = {k: v[0] / max(v[1], 1) for k, v in prof.items()}
+    t_score = stage_ms["score_bounds"] * 1e-3
+    achieved = evals * FLOP_PER_EVAL / t_score * 1e-12
+    peak_ffma = eng.measure_fp32_peak(0)
+    peak_ffma2 = eng.measure_fp32_peak(1)
+    peak = max(peak_ffma, peak_ffma2)
+    nominal = eng.sm_count * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 * 1e-12
+    roof = {"bound": "fp32", "kernel": "tv5::score_bounds", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "traffic": None,
+            "peak_source": "FP32 FMA-chain microbenchmark measured live in this run (tv5_measure_fp32_peak; "
+                           "MEASURED_PEAKS.json has no FP32 entry)",
+            "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
+            "algorithmic_flop_per_launch": evals * FLOP_PER_EVAL, "sampson_evals_per_launch": evals,
+            "sampson_evals_per_s": evals / t_score, "kernel_ms": stage_ms["score_bounds"],
+            "note": "34 FLOP per Sampson evaluation (SURVEY 8(d)); the kernel executes 40 FP32 lane-ops per evaluation "
+                    "(guard band included), so its FP32-pipe utilisation is frac * 40/34"}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        roof["hbm_gbs_measured_peak"] = peaks.get("hbm_gbs")
+    except Exception:
+        pass
+
+    # single-pair latency (stream-ordered, no host sync inside)
+    a, b = x1[:N_CORR].contiguous(), x2[:N_CORR].contiguous()
+    s0 = sets[0].contiguous()
+    for _ in range(5):
+        eng.compute_pose(a, b, ITERS, THR, sets=s0)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(50):
+        eng.compute_pose(a, b, ITERS, THR, sets=s0)
+    e1.record()
+    torch.cuda.synchronize()
+    single_ms = e0.elapsed_time(e1) / 50
+
+    # accuracy of the batch against ground truth
+    Pn = Po[:B].cpu().numpy()
+    rot = [synth.rotation_error_deg(Pn[i][:, :3], pairs[i]["R"]) for i in range(B)]
+    tr = [synth.translation_error_deg(Pn[i][:, 3], pairs[i]["t"]) for i in range(B)]
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 decisions/solver + f32 guard-band scoring", "data": "synthetic",
+            "config": config(B, f"pair-sharded dp{world}" if world > 1 else "1 GPU"),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "tv5_compute_pose_batch_host (C ABI, pinned host buffers)"},
+            "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "roofline": roof,
+            "stage_ms_per_step": stage_ms,
+            "single_pair_latency_ms": single_ms,
+            "fp32_peak_tflops": {"ffma": peak_ffma, "ffma2": peak_ffma2, "nominal": nominal},
+            "hypotheses_per_pair": M_total / B,
+            "candidates_per_pair": float(so_h[:B, 4].mean()),
+            "inliers_per_pair": float(so_h[:B, 0].mean()),
+            "pose_error_deg": {"rot_median": float(np.median(rot)), "rot_max": float(np.max(rot)),
+                               "trans_median": float(np.median(tr)), "trans_max": float(np.max(tr))}}
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per step per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) prep_points(const PairDesc* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// solve_sets: one thread per minimal set, grid (ceil(H/64), B), block 64
+// solve_sets: one thread per minimal set, grid (ceil(H/32), B), block 32
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void make_hyp32(const double* E, double inv_thr, Hyp32& h) {
   double s = 0.0;
@@ -133,7 +133,7 @@ __device__ __forceinline__ void make_hyp32(const double* E, double inv_thr, Hyp3
   h.pad = 0.f;
 }
 
-__global__ void __launch_bounds__(64) solve_sets(const PairDesc* __restrict__ desc,
+__global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ desc,
                                                  PairState* __restrict__ state, int H,
                                                  int with_cheirality, double inv_thr,
                                                  double* __restrict__ E_list,
@@ -862,7 +862,7 @@ int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, 
   stage_mark(ctx, st, 0);
   prep_points<<<dim3((max_pp + 255) / 256, B), 256, 0, st>>>(w.desc, w.state, w.pp, inv_thr);
   stage_mark(ctx, st, 1);
-  solve_sets<<<dim3((H + 63) / 64, B), 64, 0, st>>>(w.desc, w.state, H, with_cheirality, inv_thr,
+  solve_sets<<<dim3((H + 31) / 32, B), 32, 0, st>>>(w.desc, w.state, H, with_cheirality, inv_thr,
                                                    w.E_list, with_cheirality ? w.P_list : nullptr,
                                                    w.n_valid, w.n_roots, w.hyp, w.hyp_id, w.notin,
                                                    w.out);
@@ -880,7 +880,7 @@ int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, 
       pp_per_tile = std::max(64, std::min(kMaxTilePairs, t));
     }
   }
-  plan_tiles<<<1, 32, 0, st>>>(w.desc, w.state, w.ctl, B, pp_per_tile, thr, two_stage ? 0 : 1);
+  plan_tiles<<<1, 32, 0, st>>>(w.desc, w.state, w.ctl, B, pp_per_tile, thr, (two_stage || ctx->force_exact) ? 0 : 1);
   stage_mark(ctx, st, 3);
   if (!two_stage) {
     const int grid = slots;
@@ -971,7 +971,7 @@ int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, i
   TV5_CUDA(ctx, cudaMemcpyAsync(ctx->ws.desc, &d, sizeof(d), cudaMemcpyHostToDevice, st));
   TV5_CUDA(ctx, cudaMemsetAsync(E_list, 0, (size_t)H * 90 * sizeof(double), st));
   if (P_list) TV5_CUDA(ctx, cudaMemsetAsync(P_list, 0, (size_t)H * 120 * sizeof(double), st));
-  solve_sets<<<dim3((H + 63) / 64, 1), 64, 0, st>>>(ctx->ws.desc, ctx->ws.state, H, with_cheirality, 1.0,
+  solve_sets<<<dim3((H + 31) / 32, 1), 32, 0, st>>>(ctx->ws.desc, ctx->ws.state, H, with_cheirality, 1.0,
                                                    E_list, with_cheirality ? P_list : nullptr, n_valid,
                                                    n_roots, nullptr, nullptr, nullptr, nullptr);
   TV5_CUDA(ctx, cudaGetLastError());
@@ -1073,6 +1073,12 @@ int tv5_measure_fp32_peak(tv5_ctx* ctx, int mode, double* tflops_out) {
   cudaFree(sink);
   TV5_CUDA(ctx, cudaGetLastError());
   *tflops_out = best;
+  return TV5_OK;
+}
+
+int tv5_set_force_exact(tv5_ctx* ctx, int on) {
+  if (!ctx) return TV5_ERR_INVALID;
+  ctx->force_exact = on != 0;
   return TV5_OK;
 }
 

@@ -83,6 +83,7 @@ struct tv5_ctx {
   int last_cuda = 0;
   tv5::Workspace ws;
   std::vector<tv5::RngTable> rng_tables;
+  bool force_exact = false;
   bool profiling = false;
   cudaEvent_t ev[TV5_N_STAGES + 1] = {};
   double stage_ms[TV5_N_STAGES] = {};

@@ -1,0 +1,122 @@
+"""Multi-GPU execution: one process per GPU, torch.distributed for the plumbing.
+
+Two ways the path shards:
+
+* pair-sharded (config 3): image pairs are independent; rank g takes a contiguous block of
+  pairs.  No data-path collective; an optional all_gather returns every pair's 176-byte result
+  to all ranks.
+* hypothesis-sharded (config 4): one large pair, correspondences replicated, rank g scores the
+  hypothesis ids [g*H/G, (g+1)*H/G) — i.e. reference threads [g*512/G, (g+1)*512/G) — and the
+  global winner is one MAX all-reduce over a packed (count, ~id) int64 key, followed by a
+  broadcast of the owner's E and P.  The key order reproduces the reference's
+  first-maximum-over-(thread, iteration, root) rule (essential_matrix.cu:252).
+
+The reference has no counterpart: it runs under torch.nn.DataParallel (main.py:219), whose
+replicas serialise on the extension's blocking call.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REF_THREADS = 512
+_ID_BITS = 31  # key = count << 31 | (2^31 - 1 - (set * 16 + root))
+
+
+def pair_shard(n_pairs, world, rank):
+    """[start, stop) of the contiguous block of pairs owned by `rank` (balanced to +-1)."""
+    base, rem = divmod(int(n_pairs), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def hypothesis_shard(iters, world, rank):
+    """(first reference thread, number of threads, first hypothesis id) of `rank`'s share of the
+    512*iters hypotheses.  512 must be divisible by world (1, 2, 4, 8 ... GPUs)."""
+    if REF_THREADS % world:
+        raise ValueError("world size must divide 512")
+    tpr = REF_THREADS // world
+    return rank * tpr, tpr, rank * tpr * int(iters)
+
+
+def pack_key(count, set_id, root):
+    """int64 ordering key: larger count wins, then smaller (set, root)."""
+    ident = (int(set_id) << 4) | int(root)
+    return (int(count) << _ID_BITS) | ((1 << _ID_BITS) - 1 - ident)
+
+
+def unpack_key(key):
+    key = int(key)
+    count = key >> _ID_BITS
+    ident = (1 << _ID_BITS) - 1 - (key & ((1 << _ID_BITS) - 1))
+    return count, ident >> 4, ident & 15
+
+
+def reduce_winner(count, set_id, root, E, P, group=None):
+    """All ranks call this with their local winner (global hypothesis id).  Returns the global
+    (count, set, root, E, P).  E, P: tensors on the device the backend communicates on."""
+    dev = E.device
+    has = count > 0 and set_id >= 0
+    key = torch.tensor([pack_key(count, set_id, root) if has else 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(key, op=dist.ReduceOp.MAX, group=group)
+    gcount, gset, groot = unpack_key(key.item())
+    if gcount == 0:
+        return 0, -1, -1, torch.zeros_like(E), torch.zeros_like(P)
+    mine = has and gset == set_id and groot == root and gcount == count
+    # exactly one rank owns the winning id; sum-reduce its payload
+    payload = torch.cat([E.reshape(-1), P.reshape(-1)]) if mine else torch.zeros(
+        E.numel() + P.numel(), dtype=E.dtype, device=dev)
+    dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
+    return gcount, gset, groot, payload[:E.numel()].view_as(E).clone(), payload[E.numel():].view_as(P).clone()
+
+
+def compute_pose_hypothesis_sharded(engine, x1, x2, iters, thr, sets=None, with_cheirality=True,
+                                    group=None):
+    """One large pair on all ranks of `group`; x1/x2 must already be replicated.  `sets` is the
+    full [512*iters, 5] table (or None for the reference RNG table)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    t0, tpr, h0 = hypothesis_shard(iters, world, rank)
+    if sets is None:
+        sets = engine.ref_rng_sets(x1.shape[0], iters)
+    sets = sets.view(REF_THREADS * int(iters), 5)
+    local = sets[h0:h0 + tpr * int(iters)]
+    # the engine's hypothesis budget is 512 * iters_local: keep the id layout by padding the
+    # thread dimension, not the iteration dimension
+    if (tpr * int(iters)) % REF_THREADS:
+        raise ValueError("512*iters/world must be a multiple of 512 (iters divisible by world)")
+    iters_local = tpr * int(iters) // REF_THREADS
+    r = engine.compute_pose(x1, x2, iters_local, thr, sets=local.contiguous(),
+                            with_cheirality=with_cheirality)
+    lset = r.best_set
+    gset = h0 + lset if lset >= 0 else -1
+    return reduce_winner(r.count, gset, r.best_root, r.E, r.P, group=group)
+
+
+def gather_pair_results(E, P, stats, n_pairs, group=None):
+    """all_gather of pair-sharded results into [n_pairs, ...] tensors (ragged shards padded)."""
+    world = dist.get_world_size(group)
+    per = max(pair_shard(n_pairs, world, r)[1] - pair_shard(n_pairs, world, r)[0] for r in range(world))
+    dev = E.device
+
+    def pad(t, width):
+        out = torch.zeros((per, width), dtype=t.dtype, device=dev)
+        out[: t.shape[0]] = t.reshape(t.shape[0], width)
+        return out
+
+    bufs = []
+    for t, width in ((E, 9), (P, 12), (stats, 8)):
+        mine = pad(t, width)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        keep = []
+        for r in range(world):
+            a, b = pair_shard(n_pairs, world, r)
+            keep.append(parts[r][: b - a])
+        bufs.append(torch.cat(keep, 0))
+    return bufs[0].view(n_pairs, 3, 3), bufs[1].view(n_pairs, 3, 4), bufs[2]
+
+
+def shard_offsets(offsets, start, stop):
+    """Offsets of a contiguous block of pairs, rebased to 0, plus the point range."""
+    off = np.asarray(offsets, dtype=np.int64)
+    return off[start:stop + 1] - off[start], int(off[start]), int(off[stop])

@@ -249,6 +249,9 @@ class Engine:
             _check(self.ctx, self.L.tv5_measure_fp32_peak(self.ctx, int(mode), C.byref(v)), "fp32 peak")
         return v.value
 
+    def set_force_exact(self, on=True):
+        _check(self.ctx, self.L.tv5_set_force_exact(self.ctx, int(bool(on))), "set_force_exact")
+
     def profile_enable(self, on=True):
         _check(self.ctx, self.L.tv5_profile_enable(self.ctx, int(bool(on))), "profile_enable")
 

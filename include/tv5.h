@@ -163,6 +163,11 @@ int tv5_score_bounds(tv5_ctx* ctx, void* stream, const double* x1, const double*
  */
 int tv5_ref_rng_sets(tv5_ctx* ctx, void* stream, int N, int iters, int32_t* sets_out);
 
+/* Testing/diagnostic switch: on != 0 makes the pose entry points score every hypothesis with the
+ * float64 scorer (no float32 guard-band pass).  Results are identical by construction; the
+ * tests use this to prove it. */
+int tv5_set_force_exact(tv5_ctx* ctx, int on);
+
 /* Device-timed (CUDA events) measurements used by bench.py; both synchronise. */
 
 /* FP32 FMA-chain peak of this GPU in TFLOP/s: mode 0 = scalar FFMA, 1 = packed FFMA2. */

@@ -43,6 +43,11 @@ int ref_score(const double* x1, const double* x2, int n_test, const double* E_li
 // Index table drawn exactly as the reference does: curand_init(1234, tid, 0) per thread,
 // 5 x RandomInt per iteration; out[(tid*iters + it)*5 + i].  512 threads (8 x 64).
 int ref_rng_sets(int N, int iters, int32_t* out);
+
+// The reference's whole computeP on its own kernels (see ref_twin_cuda.cu); x1/x2/E_out/P_out
+// device pointers, count_out host pointer.  Synchronous.  Returns a cudaError_t.
+int ref_compute_pose(const double* x1, const double* x2, int N, int n_pre, int n_full, int iters,
+                     double thr, double* E_out, double* P_out, int32_t* count_out, int use_managed);
 #endif
 
 #ifdef __cplusplus

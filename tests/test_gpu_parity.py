@@ -1,0 +1,368 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI of
+libtv5.so (via tv5.Engine) and is checked against the CPU oracle and the committed golden
+vectors.  Tolerances are written next to each assertion."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tv5 import synth
+
+pytestmark = pytest.mark.gpu
+THR = 1e-4
+
+
+def dev(a, dtype=torch.float64):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype=dtype)
+
+
+def unpack_masks(masks, n):
+    mk = masks.cpu().numpy().view(np.uint32)
+    bits = (mk[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1
+    return bits.reshape(mk.shape[0], -1)[:, :n].astype(np.uint8)
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "solver_ref_host.npz"))
+
+
+@pytest.fixture(scope="module")
+def gold_gpu(golden_dir):
+    p = os.path.join(golden_dir, "gpu_reference.npz")
+    if not os.path.exists(p):
+        pytest.skip("gpu_reference.npz not generated yet")
+    return np.load(p)
+
+
+@pytest.fixture(scope="module")
+def std_pair():
+    sc = synth.make_pair(10000, 1234)
+    return sc, dev(sc["x1"]), dev(sc["x2"])
+
+
+# ---------------------------------------------------------------------------------------------
+# scoring: bit-exact
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 2047])
+def test_exact_score_bit_exact_vs_oracle(engine, gold, n):
+    x1, x2 = gold["kitti_x1"][:n], gold["kitti_x2"][:n]
+    E = gold["kitti_E"].reshape(-1, 9)
+    E = E[np.abs(E).sum(1) > 0][:200]
+    for thr in (1e-4, 1e-3, 0.5):
+        cnt, masks = engine.score(dev(x1), dev(x2), dev(E), thr, want_mask=True)
+        c_or, m_or = oracle.score(x1, x2, E, thr, want_mask=True)
+        assert (cnt.cpu().numpy() == c_or).all()          # integer: exact
+        assert (unpack_masks(masks, n) == m_or).all()     # bit: exact
+
+
+def test_exact_score_matches_reference_gpu_counts(engine, gold, gold_gpu):
+    """Counts of the reference's own ComputeError<double> compiled by nvcc (twin, GPU box)."""
+    for name in ("kitti", "sideways"):
+        x1, x2 = dev(gold[f"{name}_x1"]), dev(gold[f"{name}_x2"])
+        E = dev(gold_gpu[f"{name}_twin_E_list"])
+        for thr in (1e-4, 1e-3):
+            cnt = engine.score(x1, x2, E, thr).cpu().numpy()
+            assert (cnt == gold_gpu[f"{name}_twin_counts_{thr:g}"]).all()
+
+
+def test_oracle_sampson_bits_match_reference_gpu(gold, gold_gpu):
+    """Pins the oracle's operation order: raw error values of the reference kernel, bit for bit."""
+    x1, x2 = gold["sideways_x1"], gold["sideways_x2"]
+    E = gold_gpu["sideways_twin_E_list"][:48]
+    err = gold_gpu["sideways_twin_err_sample"]
+    for m in range(0, 48, 5):
+        for j, k in enumerate(range(0, x1.shape[0], 4)):
+            if j % 7:
+                continue
+            mine = oracle.sampson_err(E[m], x1[k, 0], x1[k, 1], x2[k, 0], x2[k, 1])
+            assert mine == err[m, j] or (np.isnan(mine) and np.isnan(err[m, j]))
+
+
+def test_score_edge_cases(engine):
+    x = np.tile([[0.1, 0.2]], (40, 1))
+    xn = x.copy()
+    xn[7, 0] = np.nan
+    xn[9, 1] = np.inf
+    Efwd = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 0.0]]).reshape(1, 9)
+    E = np.concatenate([Efwd, np.zeros((1, 9)), np.full((1, 9), np.nan)])
+    cnt = engine.score(dev(xn), dev(x), dev(E), 1e-9).cpu().numpy()
+    assert cnt.tolist() == oracle.score(xn, x, E, 1e-9).tolist() == [38, 0, 0]
+    # empty hypothesis list / zero points
+    assert engine.score(dev(x), dev(x), torch.zeros(0, 9, dtype=torch.float64, device="cuda"), 1.0).numel() == 0
+    assert engine.score(dev(x), dev(x), dev(Efwd), 1.0, n_test=0).cpu().tolist() == [0]
+
+
+def test_guard_band_brackets_exact_counts(engine, std_pair):
+    sc, x1, x2 = std_pair
+    sets = dev(synth.make_sets(10000, 2048, 3), torch.int32)
+    s = engine.solve5(x1, x2, sets)
+    idx = torch.arange(10, device="cuda")[None, :] < s["n_valid"][:, None]
+    E = s["E"].view(-1, 10, 9)[idx].contiguous()
+    exact = engine.score(x1, x2, E, THR)
+    for n_test in (10000, 9999, 4097, 130):
+        lo, hi = engine.score_bounds(x1, x2, E, THR, n_test=n_test)
+        ex = engine.score(x1, x2, E, THR, n_test=n_test)
+        assert bool(((lo <= ex) & (ex <= hi)).all())     # rigorous bracket, no exceptions
+    lo, hi = engine.score_bounds(x1, x2, E, THR)
+    assert float((hi - lo).float().mean()) < 0.02 * 10000  # and a useful one
+    assert int((hi >= lo.max()).sum()) < 0.05 * E.shape[0]
+    assert bool((exact <= hi).all())
+
+
+def test_guard_band_adversarial_scales(engine):
+    """Bounds must hold for unnormalised E of any magnitude, tiny thresholds' neighbours and
+    points far from the principal point."""
+    rng = np.random.default_rng(5)
+    sc = synth.make_pair(3000, seed=9, noise_px=0.3)
+    x1, x2 = sc["x1"] * 3.0, sc["x2"] * 3.0
+    Eg = sc["E_gt"] / np.linalg.norm(sc["E_gt"])
+    E = np.stack([(Eg + rng.normal(0, s, (3, 3))) * sc_ for s in (0, 1e-6, 1e-4, 1e-2) for sc_ in (1e-8, 1.0, 1e6)
+                  for _ in range(20)]).reshape(-1, 9)
+    for thr in (3e-4, 1e-3, 1e-2):
+        lo, hi = engine.score_bounds(dev(x1), dev(x2), dev(E), thr)
+        ex = engine.score(dev(x1), dev(x2), dev(E), thr)
+        assert bool(((lo <= ex) & (ex <= hi)).all())
+        assert (ex.cpu().numpy() == oracle.score(x1, x2, E, thr)).all()
+
+
+def test_guard_band_refuses_nonfinite_input(engine):
+    import tv5
+    x = np.random.default_rng(0).normal(size=(100, 2))
+    xb = x.copy()
+    xb[3, 1] = np.nan
+    with pytest.raises(tv5.Tv5Error):
+        engine.score_bounds(dev(xb), dev(x), dev(np.eye(3).reshape(1, 9)), 1e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# solver: tolerance
+# ---------------------------------------------------------------------------------------------
+def _compare_solver(mine, ref_E, ref_P, ref_nr, ref_nv, skip=2):
+    H = ref_nv.shape[0]
+    ok = np.ones(H, bool)
+    ok[:skip] = False
+    nr, nv = mine["n_roots"].cpu().numpy(), mine["n_valid"].cpu().numpy()
+    same = (nr == ref_nr) & (nv == ref_nv)
+    assert same[ok].mean() > 0.98                       # real-root / cheirality counts agree
+    sel = ok & same
+    E = mine["E"].cpu().numpy().reshape(H, 10, 9)
+    P = mine["P"].cpu().numpy().reshape(H, 10, 12)
+    dE = np.abs(E - ref_E).reshape(H, -1).max(1)[sel] / (np.abs(ref_E).reshape(H, -1).max(1)[sel] + 1)
+    dP = np.abs(P - ref_P).reshape(H, -1).max(1)[sel]
+    # unnormalised E equal in scale, sign and order; tolerance: see tests/test_oracle.py
+    assert np.median(dE) < 1e-9 and (dE < 1e-6).mean() > 0.93 and dE.max() < 5e-2
+    assert np.median(dP) < 1e-9 and (dP < 1e-6).mean() > 0.93
+
+
+@pytest.mark.parametrize("name", ["kitti", "noisefree", "sideways", "f64coords"])
+def test_solver_vs_reference_host_golden(engine, gold, name):
+    x1, x2, sets = gold[f"{name}_x1"], gold[f"{name}_x2"], gold[f"{name}_sets"]
+    mine = engine.solve5(dev(x1), dev(x2), dev(sets, torch.int32))
+    _compare_solver(mine, gold[f"{name}_E"], gold[f"{name}_P"], gold[f"{name}_n_roots"], gold[f"{name}_n_valid"])
+
+
+@pytest.mark.parametrize("name", ["kitti", "sideways"])
+def test_solver_vs_reference_gpu_golden(engine, gold, gold_gpu, name):
+    x1, x2, sets = gold[f"{name}_x1"], gold[f"{name}_x2"], gold[f"{name}_sets"]
+    mine = engine.solve5(dev(x1), dev(x2), dev(sets, torch.int32))
+    _compare_solver(mine, gold_gpu[f"{name}_twin_E"], gold_gpu[f"{name}_twin_P"], gold_gpu[f"{name}_twin_n_roots"],
+                    gold_gpu[f"{name}_twin_n_valid"])
+
+
+def test_solver_vs_oracle_large(engine, std_pair):
+    sc, x1, x2 = std_pair
+    sets = synth.make_sets(10000, 4096, 17)
+    mine = engine.solve5(x1, x2, dev(sets, torch.int32))
+    orc = oracle.solve_sets(sc["x1"], sc["x2"], sets, True)
+    _compare_solver(mine, orc["E"], orc["P"], orc["n_roots"], orc["n_valid"], skip=0)
+    ma = engine.solve5(x1, x2, dev(sets, torch.int32), with_cheirality=False)
+    oa = oracle.solve_sets(sc["x1"], sc["x2"], sets, False)
+    assert (ma["n_valid"].cpu().numpy() == oa["n_valid"]).mean() > 0.99
+    assert bool((ma["n_valid"] == ma["n_roots"]).all())
+
+
+def test_solver_outputs_are_valid_poses(engine, std_pair):
+    sc, x1, x2 = std_pair
+    s = engine.solve5(x1, x2, dev(synth.make_sets(10000, 1024, 23), torch.int32))
+    nv = s["n_valid"].cpu().numpy()
+    P = s["P"].cpu().numpy()
+    E = s["E"].cpu().numpy()
+    for h in range(0, 1024, 7):
+        for j in range(nv[h]):
+            R, t = P[h, j, :, :3], P[h, j, :, 3]
+            assert abs(np.linalg.det(R) - 1) < 1e-6 and np.abs(R @ R.T - np.eye(3)).max() < 1e-6
+            assert abs(np.linalg.norm(t) - 1) < 1e-9
+            assert synth.essential_distance(synth.essential_from_pose(R, t), E[h, j]) < 1e-6
+
+
+def test_reference_rng_table(engine, gold_gpu):
+    for key in gold_gpu.files:
+        if key.startswith("rng_"):
+            _, N, iters = key.split("_")
+            mine = engine.ref_rng_sets(int(N), int(iters)).cpu().numpy()
+            assert (mine == np.minimum(gold_gpu[key], int(N) - 1)).all()   # index table: exact
+
+
+# ---------------------------------------------------------------------------------------------
+# whole pipeline
+# ---------------------------------------------------------------------------------------------
+def _check_self_consistent(engine, x1h, x2h, r, thr, n_full=None):
+    """Size-independent properties: the reported count and mask are exactly the reference
+    Sampson decisions for the returned E, and the returned E/P are the solver's for that id."""
+    E = r.E.cpu().numpy()
+    n = x1h.shape[0] if n_full is None else n_full
+    c, m = oracle.score(x1h, x2h, E.reshape(1, 9), thr, n=n, want_mask=True)
+    assert r.count == int(c[0])
+    if r.mask is not None:
+        assert (r.mask.cpu().numpy() == m[0]).all() and int(r.mask.sum()) == r.count
+
+
+@pytest.mark.parametrize("cheir", [True, False])
+def test_pipeline_vs_oracle_ransac(engine, gold, cheir):
+    x1h, x2h = gold["kitti_x1"], gold["kitti_x2"]
+    sets = synth.make_sets(2000, 1024, 31)
+    r = engine.compute_pose(dev(x1h), dev(x2h), 2, THR, sets=dev(sets, torch.int32), with_cheirality=cheir,
+                            want_mask=True)
+    o = oracle.ransac(x1h, x2h, sets, 2, THR, with_cheirality=cheir)
+    _check_self_consistent(engine, x1h, x2h, r, THR)
+    # independent solvers differ in the last bits of E, which can move a point across the
+    # threshold: same winner, or a count within 2 of the oracle's best
+    assert (r.best_set, r.best_root) == (o["best_set"], o["best_root"]) or abs(r.count - o["count"]) <= 2
+    assert abs(r.count - o["count"]) <= 2
+    assert synth.essential_distance(r.E.cpu().numpy(), o["E"]) < 1e-4
+    if cheir:
+        assert synth.rotation_error_deg(r.P.cpu().numpy()[:, :3], o["P"][:, :3]) < 1e-2
+    else:
+        assert float(r.P.abs().sum()) == 0.0
+
+
+def test_pipeline_fast_path_equals_float64_path(engine, std_pair):
+    sc, x1, x2 = std_pair
+    sets = dev(synth.make_sets(10000, 4096, 41), torch.int32)
+    a = engine.compute_pose(x1, x2, 8, THR, sets=sets, want_mask=True)
+    engine.set_force_exact(True)
+    try:
+        b = engine.compute_pose(x1, x2, 8, THR, sets=sets, want_mask=True)
+    finally:
+        engine.set_force_exact(False)
+    assert a.fast_path == 1 and b.fast_path == 0
+    assert (a.count, a.best_set, a.best_root) == (b.count, b.best_set, b.best_root)
+    assert torch.equal(a.E, b.E) and torch.equal(a.P, b.P) and torch.equal(a.mask, b.mask)
+    assert a.n_candidates < 0.05 * a.n_hypotheses and b.n_candidates == b.n_hypotheses
+    _check_self_consistent(engine, sc["x1"], sc["x2"], a, THR)
+    # accuracy against ground truth (degrees)
+    P = a.P.cpu().numpy()
+    assert synth.rotation_error_deg(P[:, :3], sc["R"]) < 0.05
+    assert synth.translation_error_deg(P[:, 3], sc["t"]) < 0.5
+
+
+def test_pipeline_is_deterministic_and_batch_equals_single(engine):
+    ns = [10000, 9999, 777, 5, 2048]
+    pairs = [synth.make_pair(n, **{**synth.pair_variation(i), "seed": 50 + i}) for i, n in enumerate(ns)]
+    X1 = dev(np.concatenate([p["x1"] for p in pairs]))
+    X2 = dev(np.concatenate([p["x2"] for p in pairs]))
+    off = np.r_[0, np.cumsum(ns)]
+    sets = np.stack([synth.make_sets(n, 1024, 60 + i) for i, n in enumerate(ns)])
+    rb = engine.compute_pose_batch(X1, X2, off, 2, THR, sets=dev(sets, torch.int32), want_mask=True)
+    rb2 = engine.compute_pose_batch(X1, X2, off, 2, THR, sets=dev(sets, torch.int32), want_mask=True)
+    assert torch.equal(rb.E, rb2.E) and torch.equal(rb.stats[:, :3], rb2.stats[:, :3]) and torch.equal(rb.mask, rb2.mask)
+    for i, n in enumerate(ns):
+        a, b = off[i], off[i + 1]
+        rs = engine.compute_pose(X1[a:b].contiguous(), X2[a:b].contiguous(), 2, THR, sets=dev(sets[i], torch.int32),
+                                 want_mask=True)
+        assert torch.equal(rs.E, rb.E[i]) and torch.equal(rs.P, rb.P[i])
+        assert rs.count == int(rb.count[i]) and rs.best_set == int(rb.best_set[i])
+        assert torch.equal(rs.mask, rb.mask[a:b])
+        _check_self_consistent(engine, pairs[i]["x1"], pairs[i]["x2"], rs, THR)
+
+
+def test_two_stage_selection_matches_oracle(engine, gold):
+    x1h, x2h = gold["kitti_x1"], gold["kitti_x2"]
+    sets = synth.make_sets(2000, 512, 71)
+    for n_pre, n_full in ((100, 2000), (2000, 500), (10, 1000)):
+        r = engine.compute_pose(dev(x1h), dev(x2h), 1, THR, n_pre=n_pre, n_full=n_full, sets=dev(sets, torch.int32),
+                                want_mask=True)
+        o = oracle.ransac(x1h, x2h, sets, 1, THR, n_pre=n_pre, n_full=n_full)
+        assert r.fast_path == 0
+        _check_self_consistent(engine, x1h, x2h, r, THR, n_full=n_full)
+        assert abs(r.count - o["count"]) <= 2
+        assert (r.best_set, r.best_root) == (o["best_set"], o["best_root"]) or abs(r.count - o["count"]) <= 2
+
+
+def test_no_inliers_gives_zero_result(engine):
+    rng = np.random.default_rng(3)
+    x1h, x2h = rng.uniform(-1, 1, (200, 2)), rng.uniform(-1, 1, (200, 2))
+    r = engine.compute_pose(dev(x1h), dev(x2h), 1, 1e-12, sets=dev(synth.make_sets(200, 512, 1), torch.int32))
+    if r.count == 0:
+        assert r.best_set == -1 and float(r.E.abs().sum()) == 0.0
+    else:
+        _check_self_consistent(engine, x1h, x2h, r, 1e-12)
+
+
+def test_reference_rng_default_and_reference_extension_golden(engine, std_pair, gold, gold_gpu):
+    """sets=None must behave like the reference: same index table, and - when the golden file
+    holds outputs of the unmodified extension - same winner within tolerance."""
+    sc, x1, x2 = std_pair
+    r = engine.compute_pose(x1, x2, 8, THR)
+    tab = engine.ref_rng_sets(10000, 8)
+    r2 = engine.compute_pose(x1, x2, 8, THR, sets=tab)
+    assert torch.equal(r.E, r2.E) and r.count == r2.count
+    _check_self_consistent(engine, sc["x1"], sc["x2"], r, THR)
+    key = "refext_std10k_8_count"
+    if key in gold_gpu.files:
+        assert abs(r.count - int(gold_gpu[key])) <= 3
+        assert synth.essential_distance(r.E.cpu().numpy(), gold_gpu["refext_std10k_8_E"]) < 1e-4
+        assert synth.rotation_error_deg(r.P.cpu().numpy()[:, :3], gold_gpu["refext_std10k_8_P"][:, :3]) < 1e-2
+        # and the reference's own count is exactly our exact score of the reference's E
+        c = engine.score(x1, x2, dev(gold_gpu["refext_std10k_8_E"].reshape(1, 9)), THR)
+        assert int(c[0]) == int(gold_gpu[key])
+
+
+def test_full_size_dense_pair_properties(engine):
+    """Config-4 shape (453,620 correspondences); properties only, the oracle would take minutes."""
+    sc = synth.make_pair(dense=True, seed=4)
+    x1, x2 = dev(sc["x1"]), dev(sc["x2"])
+    sets = dev(synth.make_sets(sc["x1"].shape[0], 1024, 5), torch.int32)
+    r = engine.compute_pose(x1, x2, 2, THR, sets=sets, want_mask=True)
+    assert r.fast_path == 1 and int(r.mask.sum()) == r.count
+    c = engine.score(x1, x2, r.E.reshape(1, 9), THR)
+    assert int(c[0]) == r.count
+    P = r.P.cpu().numpy()
+    assert synth.rotation_error_deg(P[:, :3], sc["R"]) < 0.05 and synth.translation_error_deg(P[:, 3], sc["t"]) < 0.5
+    assert r.count > 0.6 * sc["inlier_gt"].sum()
+
+
+# ---------------------------------------------------------------------------------------------
+# drop-in module
+# ---------------------------------------------------------------------------------------------
+def test_shim_computeP_contract(std_pair):
+    import essential_matrix as em
+    sc, x1, x2 = std_pair
+    E, P, n = em.computeP(x1, x2, 10000, 10000, 5, THR)
+    assert E.shape == (3, 3) and P.shape == (3, 4) and E.dtype == torch.float64 and E.is_cuda and P.is_cuda
+    assert int(n) > 5000 and n == int(n) and f"{n}" == str(int(n))
+    E2 = em.initialise(x1, x2, 10000, 10000, 5, THR)
+    assert E2.shape == (3, 3) and E2.is_cuda
+    for bad, msg in ((x1.cpu(), "input1 must be a CUDA tensor"), (x1.float(), "input1 must be a double tensor"),
+                     (x1.t().contiguous().t(), "input1 must be contiguous")):
+        with pytest.raises(RuntimeError, match=msg):
+            em.computeP(bad, x2, 10000, 10000, 5, THR)
+
+
+def test_shim_in_sfmnet_call_shape(std_pair):
+    """The call sequence of epipolar_utils.compute_P_matrix_ransac (epipolar_utils.py:112-135)
+    with float32 inputs, as models/SFMnet.py:259-270 produces them."""
+    import essential_matrix as em
+    sc, x1, x2 = std_pair
+    c1, c2 = x1.float(), x2.float()
+    K = torch.tensor(sc["K"], dtype=torch.float32, device="cuda")
+    Kinv = torch.inverse(K)
+    E, P, n = em.computeP(c1.double(), c2.double(), c1.shape[0], c1.shape[0], 5, THR)
+    E = E.float()
+    F = Kinv.t() @ E @ Kinv
+    assert F.shape == (3, 3) and torch.isfinite(F).all() and torch.isfinite(P).all()
+    Pm = P.cpu().numpy()
+    assert synth.rotation_error_deg(Pm[:, :3], sc["R"]) < 0.05
