@@ -26,6 +26,10 @@
 
 namespace tv5 {
 
+#ifdef TV5_SOLVE_PROFILE
+__device__ unsigned long long g_solve_prof[8];
+#endif
+
 // Completion rows of the 9x9 system (filled by tv5_create from the recurrence
 // ran <- 3.18730379 * ran; ran <- 2 (ran - floor(ran)) - 1, started at 3.18730379).
 __constant__ double c_completion[4][9];
@@ -190,29 +194,51 @@ __device__ inline void build_constraints(const double (&B)[4][9], double (*M)[20
 // 3. Gauss-Jordan on columns 0..9 (only rows 4..9 are needed afterwards)
 // ------------------------------------------------------------------------------------------
 __device__ inline bool eliminate(double (*M)[20]) {
+  // Fully unrolled over the pivot column so that every inner loop has compile-time bounds and
+  // addresses; the only dynamic index is the pivot row p.
+  bool ok = true;
+#pragma unroll
   for (int c = 0; c < 10; ++c) {
     int p = c;
     double best = fabs(M[c][c]);
+#pragma unroll
     for (int r = c + 1; r < 10; ++r) {
       const double v = fabs(M[r][c]);
       if (v > best) { best = v; p = r; }
     }
-    if (!(best > 1e-300) || !(best < 1e300)) return false;
-    if (p != c)
-      for (int j = c; j < 20; ++j) { const double t = M[c][j]; M[c][j] = M[p][j]; M[p][j] = t; }
-    const double inv = 1.0 / M[c][c];
-    for (int j = c + 1; j < 20; ++j) M[c][j] *= inv;
+    ok = ok && (best > 1e-300) && (best < 1e300);
+    double prow[20];
+#pragma unroll
+    for (int j = c; j < 20; ++j) prow[j] = M[p][j];
+    if (p != c) {
+#pragma unroll
+      for (int j = c; j < 20; ++j) M[p][j] = M[c][j];
+    }
+    const double inv = 1.0 / prow[c];
+#pragma unroll
+    for (int j = c + 1; j < 20; ++j) prow[j] *= inv;
+#pragma unroll
+    for (int j = c + 1; j < 20; ++j) M[c][j] = prow[j];
+#pragma unroll
     for (int r = c + 1; r < 10; ++r) {
       const double f = M[r][c];
-      for (int j = c + 1; j < 20; ++j) M[r][j] = fma(-f, M[c][j], M[r][j]);
+#pragma unroll
+      for (int j = c + 1; j < 20; ++j) M[r][j] = fma(-f, prow[j], M[r][j]);
     }
   }
-  for (int c = 9; c >= 5; --c)
+  if (!ok) return false;
+#pragma unroll
+  for (int c = 9; c >= 5; --c) {
+    double prow[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) prow[j] = M[c][10 + j];
+#pragma unroll
     for (int r = 4; r < c; ++r) {
       const double f = M[r][c];
 #pragma unroll
-      for (int j = 10; j < 20; ++j) M[r][j] = fma(-f, M[c][j], M[r][j]);
+      for (int j = 0; j < 10; ++j) M[r][10 + j] = fma(-f, prow[j], M[r][10 + j]);
     }
+  }
   return true;
 }
 
@@ -355,7 +381,7 @@ __device__ inline double refine_root(const SturmChain& s, double lo, double hi, 
     if ((flo < 0.0) == (fhi < 0.0)) return 0.5 * (lo + hi);
   }
   double x = 0.5 * (lo + hi);
-  for (int it = 0; it < 100; ++it) {
+  for (int it = 0; it < 48; ++it) {
     double f = p[10], df = 0.0;
 #pragma unroll
     for (int i = 9; i >= 0; --i) { df = fma(df, x, f); f = fma(f, x, p[i]); }
@@ -364,14 +390,16 @@ __device__ inline double refine_root(const SturmChain& s, double lo, double hi, 
     double xn = x - f / df;
     if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
     if (!(xn > lo && xn < hi)) return x;  // bracket collapsed to neighbouring doubles
-    if (fabs(xn - x) <= 2.3e-16 * fabs(xn)) return xn;
+    if (fabs(xn - x) <= 1.0e-15 * fabs(xn)) return xn;
     x = xn;
   }
   return x;
 }
 
 // roots ascending; returns the count.  poly[0..10] ascending powers of w.
-__device__ inline int real_roots_deg10(const double (&poly)[11], double (&roots)[10]) {
+// Generic (variable-degree chain, local-memory) implementation: used only when a Sturm
+// remainder loses more than one degree (degenerate polynomials).
+__device__ __noinline__ int real_roots_deg10_generic(const double (&poly)[11], double (&roots)[10]) {
   const double lead = poly[10];
   if (lead == 0.0) return 0;
   SturmChain s;
@@ -438,6 +466,204 @@ __device__ inline int real_roots_deg10(const double (&poly)[11], double (&roots)
       for (int i = 0; i < n && nr < 10; ++i) roots[nr++] = mid;
     }
   }
+  const double back = 1.0 / fac;
+  for (int i = 0; i < nr; ++i) roots[i] *= back;
+  return nr;
+}
+
+// ------------------------------------------------------------------------------------------
+// 5b. fast path: the generic situation where every Sturm remainder drops exactly one degree.
+//     All loops have compile-time bounds, so the 66 chain coefficients live in registers and a
+//     sign-change count is 55 independent-ish FMAs instead of 55 dependent local-memory loads.
+//     Control flow is kept warp-friendly: one flat isolation loop (one Sturm count per trip),
+//     then one bracketed Newton loop per root.
+// ------------------------------------------------------------------------------------------
+#ifdef TV5_SOLVE_PROFILE
+#define TV5_RTICK(i) do { if ((threadIdx.x & 31) == 0) { long long t__ = clock64(); atomicAdd(&g_solve_prof[i], (unsigned long long)(t__ - rt_prev)); rt_prev = t__; } } while (0)
+#else
+#define TV5_RTICK(i)
+#endif
+struct FastChain {
+  double c[11][11];  // member k has degree 10-k; only c[k][0 .. 10-k] is used
+};
+
+__device__ __forceinline__ int fast_changes(const FastChain& s, double x) {
+  double f[11];
+#pragma unroll
+  for (int k = 0; k <= 10; ++k) {
+    double v = s.c[k][10 - k];
+#pragma unroll
+    for (int i = 9 - k; i >= 0; --i) v = fma(v, x, s.c[k][i]);
+    f[k] = v;
+  }
+  int ch = 0;
+#pragma unroll
+  for (int k = 1; k <= 10; ++k) ch += (f[k - 1] == 0.0 || f[k - 1] * f[k] < 0.0) ? 1 : 0;
+  return ch;
+}
+
+__device__ __forceinline__ int fast_changes_inf(const FastChain& s, bool neg) {
+  int ch = 0;
+#pragma unroll
+  for (int k = 1; k <= 10; ++k) {
+    double a = s.c[k - 1][11 - k], b = s.c[k][10 - k];
+    if (neg && ((11 - k) & 1)) a = -a;
+    if (neg && ((10 - k) & 1)) b = -b;
+    ch += (a == 0.0 || a * b < 0.0) ? 1 : 0;
+  }
+  return ch;
+}
+
+// returns false if some remainder's leading coefficient is negligible (-> generic path)
+__device__ __forceinline__ bool fast_build(FastChain& s) {
+  const double kSmall = 1.0e-12;
+  {
+    const double f = fabs(s.c[0][10] * 10.0);
+#pragma unroll
+    for (int i = 1; i <= 10; ++i) s.c[1][i - 1] = s.c[0][i] * i / f;
+  }
+  bool ok = true;
+#pragma unroll
+  for (int k = 2; k <= 10; ++k) {
+    const int dv = 11 - k;             // degree of member k-1; member k-2 has degree dv+1
+    const double lead = s.c[k - 1][dv];  // +-1
+    double r[12];
+#pragma unroll
+    for (int i = 0; i <= dv + 1; ++i) r[i] = s.c[k - 2][i];
+    const double f1 = r[dv + 1] * lead;
+#pragma unroll
+    for (int j = 0; j < dv; ++j) r[j + 1] = fma(-f1, s.c[k - 1][j], r[j + 1]);
+    const double f0 = r[dv] * lead;
+#pragma unroll
+    for (int j = 0; j < dv; ++j) r[j] = fma(-f0, s.c[k - 1][j], r[j]);
+    if (k == 10) {
+      s.c[10][0] = -r[0];
+    } else {
+      const double top = fabs(r[dv - 1]);
+      ok = ok && (top >= kSmall);
+      const double g = -1.0 / top;
+#pragma unroll
+      for (int i = 0; i < dv; ++i) s.c[k][i] = r[i] * g;
+    }
+  }
+  return ok;
+}
+
+__device__ __forceinline__ void eval_p_dp(const double (&p)[11], double x, double& f, double& df) {
+  f = p[10];
+  df = 0.0;
+#pragma unroll
+  for (int i = 9; i >= 0; --i) { df = fma(df, x, f); f = fma(f, x, p[i]); }
+}
+
+// one root isolated in [lo,hi] by the Sturm counts (vlo - vhi == 1)
+__device__ __forceinline__ double fast_refine(const FastChain& s, double lo, double hi, int vlo) {
+  const double (&p)[11] = s.c[0];
+  double flo, fhi, d;
+  eval_p_dp(p, lo, flo, d);
+  eval_p_dp(p, hi, fhi, d);
+  if (flo == 0.0) return lo;
+  if (fhi == 0.0) return hi;
+  if ((flo < 0.0) == (fhi < 0.0)) {  // rare: no sign change at the ends; shrink with Sturm counts
+    for (int it = 0; it < 60; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      if (!(mid > lo && mid < hi)) break;
+      double fm;
+      eval_p_dp(p, mid, fm, d);
+      if (vlo - fast_changes(s, mid) == 0) { lo = mid; flo = fm; } else { hi = mid; fhi = fm; }
+      if ((flo < 0.0) != (fhi < 0.0)) break;
+    }
+    if ((flo < 0.0) == (fhi < 0.0)) return 0.5 * (lo + hi);
+  }
+  // bracketed Newton (bisect when Newton leaves the bracket or converges too slowly)
+  double xl = flo < 0.0 ? lo : hi, xh = flo < 0.0 ? hi : lo;
+  double x = 0.5 * (lo + hi), dxold = fabs(hi - lo), dx = dxold, f, df;
+  eval_p_dp(p, x, f, df);
+  for (int it = 0; it < 64; ++it) {
+    const bool bisect = (((x - xh) * df - f) * ((x - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df));
+    dxold = dx;
+    if (bisect) { dx = 0.5 * (xh - xl); x = xl + dx; } else { dx = f / df; x -= dx; }
+    if (!(fabs(dx) > 1.0e-15 * fabs(x))) break;
+    eval_p_dp(p, x, f, df);
+    if (f == 0.0) break;
+    if (f < 0.0) xl = x; else xh = x;
+  }
+  return x;
+}
+
+// roots ascending; returns the count.  poly[0..10] ascending powers of w.
+__device__ inline int real_roots_deg10(const double (&poly)[11], double (&roots)[10]) {
+  const double lead = poly[10];
+  if (lead == 0.0) return 0;
+#ifdef TV5_SOLVE_PROFILE
+  long long rt_prev = clock64();
+#endif
+  FastChain s;
+  const double inv = 1.0 / lead;
+  bool finite = true;
+#pragma unroll
+  for (int i = 0; i <= 10; ++i) {
+    s.c[0][i] = poly[i] * inv;
+    finite = finite && (fabs(s.c[0][i]) < 1e300);
+  }
+  if (!finite) return 0;
+  s.c[0][10] = 1.0;
+  double fac = 1.0;
+  const double val0 = fabs(s.c[0][0]);
+  if (val0 > 10.0) {  // same variable scaling rule as the generic path
+    fac = exp2(-0.1 * log2(val0));
+    double mult = fac;
+#pragma unroll
+    for (int i = 9; i >= 0; --i) { s.c[0][i] *= mult; mult *= fac; }
+  }
+  if (!fast_build(s)) return real_roots_deg10_generic(poly, roots);
+  TV5_RTICK(6);
+  if (fast_changes_inf(s, true) - fast_changes_inf(s, false) <= 0) return 0;
+  double bound = 0.0;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) bound = fmax(bound, fabs(s.c[0][i]));
+  bound += 1.0;
+  const int vlo0 = fast_changes(s, -bound), vhi0 = fast_changes(s, bound);
+  if (vlo0 - vhi0 <= 0) return 0;
+
+  // flat isolation loop: every trip performs exactly one Sturm count
+  double slo[12], shi[12], ilo[10], ihi[10];
+  int svlo[12], svhi[12], ivlo[10];
+  int sp = 1, ni = 0;
+  slo[0] = -bound; shi[0] = bound; svlo[0] = vlo0; svhi[0] = vhi0;
+  int nr = 0;
+  for (int trip = 0; trip < 400 && sp > 0; ++trip) {
+    const int t = sp - 1;
+    const int n = svlo[t] - svhi[t];
+    if (n <= 0) { --sp; continue; }
+    if (n == 1) {
+      if (ni < 10) { ilo[ni] = slo[t]; ihi[ni] = shi[t]; ivlo[ni] = svlo[t]; ++ni; }
+      --sp;
+      continue;
+    }
+    const double lo = slo[t], hi = shi[t];
+    const double mid = 0.5 * (lo + hi);
+    if (!(mid > lo && mid < hi) || ni + n > 10) {  // unresolvable cluster: report at the midpoint
+      for (int i = 0; i < n && ni < 10; ++i) { ilo[ni] = mid; ihi[ni] = mid; ivlo[ni] = -1; ++ni; }
+      --sp;
+      continue;
+    }
+    const int vmid = fast_changes(s, mid);
+    const int n1 = svlo[t] - vmid, n2 = vmid - svhi[t];
+    if (n1 > 0 && n2 > 0 && sp < 12) {   // split: right half below, left half on top (popped first)
+      const int vhi = svhi[t];
+      slo[t] = mid; svlo[t] = vmid;                       // right: [mid, hi]
+      slo[sp] = lo; shi[sp] = mid; svlo[sp] = n1 + vmid; svhi[sp] = vmid; ++sp;
+      (void)vhi;
+    } else if (n1 == 0) {
+      slo[t] = mid; svlo[t] = vmid;
+    } else {
+      shi[t] = mid; svhi[t] = vmid;
+    }
+  }
+  TV5_RTICK(7);
+  for (int i = 0; i < ni; ++i)
+    roots[nr++] = ivlo[i] < 0 ? ilo[i] : fast_refine(s, ilo[i], ihi[i], ivlo[i]);
   const double back = 1.0 / fac;
   for (int i = 0; i < nr; ++i) roots[i] *= back;
   return nr;
@@ -524,7 +750,7 @@ __device__ inline bool pose_from_essential(const double (&E)[9], const double (&
     bE[2][j] = b[0] * E[3 + j] - b[1] * E[j];
   }
   const double inv = 1.0 / half_tr;
-  const double bn = 1.0 / sqrt(half_tr);
+  const double bn = 1.0 / sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);  // exactly unit t
   const double t[3] = {b[0] * bn, b[1] * bn, b[2] * bn};
   // |b|^2 R = Cof(E)^T -+ [b]x E : the two rotations of the twisted pair
 #pragma unroll
@@ -554,6 +780,24 @@ __device__ inline bool pose_from_essential(const double (&E)[9], const double (&
     if (front == 10) sgn = 1.0;
     else if (behind == 10) sgn = -1.0;
     else continue;
+    // E from an ill-conditioned root is only approximately essential, and the closed form then
+    // returns an R that is only approximately orthonormal: re-orthonormalise (Gram-Schmidt on
+    // the first two rows, third by cross product), as the reference's Givens construction
+    // guarantees by design.  For a proper E this changes R at the 1e-16 level.
+    {
+      double n0 = 1.0 / sqrt(R[0][0] * R[0][0] + R[0][1] * R[0][1] + R[0][2] * R[0][2]);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) R[0][j] *= n0;
+      const double d = R[1][0] * R[0][0] + R[1][1] * R[0][1] + R[1][2] * R[0][2];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) R[1][j] -= d * R[0][j];
+      const double n1 = 1.0 / sqrt(R[1][0] * R[1][0] + R[1][1] * R[1][1] + R[1][2] * R[1][2]);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) R[1][j] *= n1;
+      R[2][0] = R[0][1] * R[1][2] - R[0][2] * R[1][1];
+      R[2][1] = R[0][2] * R[1][0] - R[0][0] * R[1][2];
+      R[2][2] = R[0][0] * R[1][1] - R[0][1] * R[1][0];
+    }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       P[4 * i] = R[i][0]; P[4 * i + 1] = R[i][1]; P[4 * i + 2] = R[i][2];
@@ -568,6 +812,12 @@ __device__ inline bool pose_from_essential(const double (&E)[9], const double (&
 // driver: one minimal set.  E_out/P_out are per-thread global slices [10][9] / [10][12].
 // Returns n_valid (after cheirality when requested); n_roots_out receives the real-root count.
 // ------------------------------------------------------------------------------------------
+#ifdef TV5_SOLVE_PROFILE
+#define TV5_TICK(i) do { if ((threadIdx.x & 31) == 0) { long long t__ = clock64(); atomicAdd(&g_solve_prof[i], (unsigned long long)(t__ - t_prev)); t_prev = t__; } } while (0)
+#else
+#define TV5_TICK(i)
+#endif
+
 __device__ inline int solve_minimal_set(const double (&q)[5][2], const double (&qp)[5][2],
                                         bool with_cheirality, double* E_out, double* P_out,
                                         int* n_roots_out) {
@@ -575,20 +825,28 @@ __device__ inline int solve_minimal_set(const double (&q)[5][2], const double (&
   double Bp[3][3][5];
   double poly[11];
   *n_roots_out = 0;
+#ifdef TV5_SOLVE_PROFILE
+  long long t_prev = clock64();
+#endif
   {
     double M[10][20];
     nullspace_basis(q, qp, B);
+    TV5_TICK(0);
     bool ok = true;
 #pragma unroll
     for (int c = 0; c < 9; ++c) ok = ok && (fabs(B[3][c]) <= 1.0);  // false on NaN (degenerate set)
     if (!ok) return 0;
     build_constraints(B, M);
+    TV5_TICK(1);
     if (!eliminate(M)) return 0;
     hidden_matrix(M, Bp);
+    TV5_TICK(2);
   }
   hidden_determinant(Bp, poly);
+  TV5_TICK(3);
   double roots[10];
   const int nr = real_roots_deg10(poly, roots);
+  TV5_TICK(4);
   *n_roots_out = nr;
   int nv = 0;
   for (int i = 0; i < nr; ++i) {
@@ -604,6 +862,7 @@ __device__ inline int solve_minimal_set(const double (&q)[5][2], const double (&
     for (int c = 0; c < 9; ++c) E_out[9 * nv + c] = E[c];
     ++nv;
   }
+  TV5_TICK(5);
   return nv;
 }
 

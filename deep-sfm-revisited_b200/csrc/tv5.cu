@@ -101,9 +101,12 @@ __global__ void __launch_bounds__(256) prep_points(const PairDesc* __restrict__ 
     o.x2s = make_float2((float)(a2.x * inv_thr), (float)(b2.x * inv_thr));
     o.y2s = make_float2((float)(a2.y * inv_thr), (float)(b2.y * inv_thr));
     pp[d.pp_off + g] = o;
-    const double s1 = fmax(a1.x * a1.x + a1.y * a1.y, b1.x * b1.x + b1.y * b1.y) + 1.0;
-    const double s2 = fmax(a2.x * a2.x + a2.y * a2.y, b2.x * b2.x + b2.y * b2.y) + 1.0;
-    bad = !(s1 < 1e30) || !(s2 < 1e30);  // catches NaN and Inf as well
+    const double s1a = a1.x * a1.x + a1.y * a1.y, s1b = b1.x * b1.x + b1.y * b1.y;
+    const double s2a = a2.x * a2.x + a2.y * a2.y, s2b = b2.x * b2.x + b2.y * b2.y;
+    // !(x < big) catches NaN and Inf as well (fmax alone would drop a NaN operand)
+    bad = !(s1a < 1e30) || !(s1b < 1e30) || !(s2a < 1e30) || !(s2b < 1e30);
+    const double s1 = fmax(s1a, s1b) + 1.0;
+    const double s2 = fmax(s2a, s2b) + 1.0;
     r1 = __double2float_ru(s1);
     r2 = __double2float_ru(s2);
   }
@@ -980,10 +983,11 @@ int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, i
 
 int tv5_score(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int n_test,
               const double* E_list, int M, double thr, int32_t* counts, uint32_t* masks) {
-  if (!ctx || !x1 || !x2 || n_test < 0 || !E_list || M < 0 || !counts) return TV5_ERR_INVALID;
+  if (!ctx || n_test < 0 || M < 0) return TV5_ERR_INVALID;
+  if (M == 0) return TV5_OK;
+  if (!E_list || !counts || (n_test > 0 && (!x1 || !x2))) return TV5_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (M == 0) return TV5_OK;
   TV5_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)M * sizeof(int32_t), st));
   if (n_test == 0) return TV5_OK;
   for (int m0 = 0; m0 < M; m0 += 65535) {

@@ -5,9 +5,10 @@
 #
 #   oracle/_ref/refext/essential_matrix*.so  unmodified reference extension, compiled directly with nvcc/g++
 #   oracle/_ref/libref_twin_cuda.so          instrumented twin, nvcc, sm_100a (GPU box only)
+#   oracle/_ref/libref_kernel.so             the reference's RANSAC kernels + restated host flow (ref_compute_pose)
 #   oracle/_ref/libref_host.so               reference solver+cheirality host-compiled with g++
 #
-# usage: oracle/build_ref.sh [host|twin|ext|all]     (twin and ext take ~10 min each)
+# usage: oracle/build_ref.sh [host|twin|kernel|ext|all]     (twin and ext take ~10 min each)
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF=/root/reference/RANSAC_FiveP
@@ -28,6 +29,13 @@ build_twin() {
        -I"$REF/essential_matrix" -I"$HERE/ref_twin" \
        "$HERE/ref_twin/ref_twin_cuda.cu" -o "$OUT/libref_twin_cuda.so"
   echo "built $OUT/libref_twin_cuda.so"
+}
+build_kernel() {
+  nvcc -O3 -std=c++17 -shared -Xcompiler -fPIC -w ${REF_KERNEL_FLAGS:-} \
+       -gencode arch=compute_100a,code=sm_100a \
+       -I"$REF/essential_matrix" -I"$HERE/ref_twin" \
+       "$HERE/ref_twin/ref_kernel.cu" -o "${REF_KERNEL_OUT:-$OUT/libref_kernel.so}"
+  echo "built ${REF_KERNEL_OUT:-$OUT/libref_kernel.so}"
 }
 build_ext() {
   # Direct compile of the reference's two translation units (no setup.py): same defines and
@@ -54,5 +62,6 @@ case "$WHAT" in
   host) build_host ;;
   twin) build_twin ;;
   ext)  build_ext ;;
-  all)  build_host; build_twin & build_ext & wait ;;
+  kernel) build_kernel ;;
+  all)  build_host; build_twin & build_kernel & build_ext & wait ;;
 esac
