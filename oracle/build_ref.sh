@@ -14,6 +14,12 @@ HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF=/root/reference/RANSAC_FiveP
 OUT="$HERE/_ref"
 WHAT="${1:-all}"
+# Device-code optimisation level of the two builds that contain the reference's RANSAC kernel
+# (EstimateProjectionMatrix<5>).  With nvcc 12.9's default (-Xcicc -O3) that kernel dies on
+# sm_100a with cudaErrorIllegalAddress at the first cudaDeviceSynchronize
+# (essential_matrix.cu:248) for every input we tried, also with -Xptxas -O1; built with
+# -Xcicc -O1 (or -G) it runs and returns the expected result.  See DESIGN.md "reference on B200".
+REF_DEVICE_OPT="${REF_DEVICE_OPT:--Xcicc -O1}"
 mkdir -p "$OUT"
 if [ ! -d "$REF" ]; then echo "reference not present at $REF; nothing to build" >&2; exit 0; fi
 
@@ -31,7 +37,7 @@ build_twin() {
   echo "built $OUT/libref_twin_cuda.so"
 }
 build_kernel() {
-  nvcc -O3 -std=c++17 -shared -Xcompiler -fPIC -w ${REF_KERNEL_FLAGS:-} \
+  nvcc -O3 -std=c++17 -shared -Xcompiler -fPIC -w ${REF_KERNEL_FLAGS:-$REF_DEVICE_OPT} \
        -gencode arch=compute_100a,code=sm_100a \
        -I"$REF/essential_matrix" -I"$HERE/ref_twin" \
        "$HERE/ref_twin/ref_kernel.cu" -o "${REF_KERNEL_OUT:-$OUT/libref_kernel.so}"
@@ -50,7 +56,7 @@ build_ext() {
   local incs="-I$torch_dir/include -I$torch_dir/include/torch/csrc/api/include -I/usr/local/cuda/include -I$py_inc"
   /usr/bin/g++ -O2 -fPIC -std=c++17 -w $defs $incs -c "$REF/essential_matrix/essential_matrix_wrapper.cpp" -o "$tmp/wrapper.o" &
   nvcc -ccbin /usr/bin/g++ -std=c++17 -w --expt-relaxed-constexpr -Xcompiler -fPIC $defs $incs \
-       -gencode=arch=compute_100a,code=sm_100a -c "$REF/essential_matrix/essential_matrix.cu" -o "$tmp/em.o"
+       $REF_DEVICE_OPT -gencode=arch=compute_100a,code=sm_100a -c "$REF/essential_matrix/essential_matrix.cu" -o "$tmp/em.o"
   wait
   nvcc -ccbin /usr/bin/g++ -shared -cudart static "$tmp/wrapper.o" "$tmp/em.o" \
        -L"$torch_dir/lib" -lc10 -ltorch -ltorch_cpu -ltorch_python -lc10_cuda -ltorch_cuda \
