@@ -31,7 +31,8 @@ H = 512 * ITERS
 THR = 1e-4
 PAIRS_PER_GPU = 256
 FLOP_PER_EVAL = 34        # 15 FMA + 3 MUL + 1 compare
-KERNELS_PER_STEP = 7      # prep, solve, plan, score_bounds, pick_candidates, exact_counts, finalize
+KERNELS_PER_STEP = 11     # prep_norms, band_consts, prep_points, solve_sets, plan_tiles, score_bounds,
+                          # pick_top, exact_counts, pick_rest, exact_counts, finalize
 METRIC = "two-view E+pose pair-solves/s @10k corr x 4096 hyp"
 UNIT = "pairs/s"
 
@@ -161,7 +162,7 @@ if mode == "ext":
         E, P, c = m.computeP(a, b, N, N, iters, thr)
         return int(c)
 else:
-    T = C.CDLL(os.path.join(root, "oracle", "_ref", "libref_twin_cuda.so"))
+    T = C.CDLL(os.path.join(root, "oracle", "_ref", "libref_kernel.so"))
     vp = C.c_void_p
     T.ref_compute_pose.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp, C.POINTER(C.c_int32), C.c_int]
     E = torch.empty(9, dtype=torch.float64, device="cuda"); P = torch.empty(12, dtype=torch.float64, device="cuda")
@@ -195,10 +196,11 @@ def run_reference(args):
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config(pairs_per_step, "single GPU, one pair per call (rank 0 only)")}
     tried = []
-    for mode, what in (("ext", "unmodified reference extension (oracle/_ref/refext), essential_matrix.computeP per pair"),
+    opt = "device code built with -Xcicc -O1: nvcc 12.9's default -O3 build of this kernel faults on sm_100a (DESIGN.md section 7)"
+    for mode, what in (("ext", "unmodified reference extension sources (oracle/_ref/refext), essential_matrix.computeP per pair; " + opt),
                        ("twin_managed", "reference kernels SetupRandomState + EstimateProjectionMatrix<5> driven by the host "
-                                        "flow of essential_matrix.cu:190-280 restated in oracle/ref_twin (managed memory)"),
-                       ("twin", "same, with cudaMalloc instead of cudaMallocManaged")):
+                                        "flow of essential_matrix.cu:190-280 restated in oracle/ref_twin/ref_kernel.cu (managed memory); " + opt),
+                       ("twin", "same, with cudaMalloc instead of cudaMallocManaged; " + opt)):
         try:
             pr = subprocess.run([sys.executable, "-c", REF_WORKER, ROOT, mode, str(args.steps), str(args.warmup), str(pairs_per_step)],
                                 capture_output=True, text=True, timeout=1500)
@@ -337,8 +339,8 @@ def run_ours(args):
             "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
             "algorithmic_flop_per_launch": evals * FLOP_PER_EVAL, "sampson_evals_per_launch": evals,
             "sampson_evals_per_s": evals / t_score, "kernel_ms": stage_ms["score_bounds"],
-            "note": "34 FLOP per Sampson evaluation (SURVEY 8(d)); the kernel executes 40 FP32 lane-ops per evaluation "
-                    "(guard band included), so its FP32-pipe utilisation is frac * 40/34"}
+            "note": "34 FLOP per Sampson evaluation (SURVEY 8(d)); the kernel executes 34 FP32 lane-ops per evaluation (17 FFMA2 per two evaluations) "
+                    "(guard band included), so its FP32-pipe utilisation is about frac"}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         roof["hbm_gbs_measured_peak"] = peaks.get("hbm_gbs")

@@ -1,13 +1,14 @@
 // tv5.cu — kernels and C ABI of libtv5 (see include/tv5.h).  sm_100a only.
 //
 // Pipeline of one submission (B image pairs, everything stream-ordered, no host sync):
-//   prep_points     float64 [N,2] x2  ->  packed float32 point pairs + per-pair norm bounds
+//   prep_norms      per-pair norm bounds; band_consts: guard-band constants per pair
+//   prep_points     float64 [N,2] x2  ->  packed float32 point pairs
 //   solve_sets      one minimal set per thread (solve5.cuh) -> E/P lists + float32 hypotheses
 //   plan_tiles      per-pair guard-band constants, scoring tile table (single CTA)
 //   score_bounds    float32 FFMA2 guard-band scorer (the roofline kernel), persistent CTAs,
 //                   correspondence tiles staged in shared memory by cp.async.bulk (TMA)
-//   pick_candidates hypotheses whose upper bound reaches the best lower bound
-//   exact_counts    float64 re-score of the candidates with the reference's exact sequence
+//   pick_top        hypothesis with the largest upper bound  -> exact_counts (float64)
+//   pick_rest       hypotheses whose upper bound reaches that exact count -> exact_counts
 //   finalize        first-max selection (count desc, hypothesis id asc), E/P/mask output
 #include <cuda_runtime.h>
 #include <curand_kernel.h>
@@ -77,11 +78,10 @@ __device__ __forceinline__ int warp_sum(int v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// prep_points: grid (ceil(max_pp / 256), B)
+// prep_norms: grid (ceil(max_pp / 256), B) — max ||(x,1)||^2 per image pair, non-finite flag
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prep_points(const PairDesc* __restrict__ desc,
-                                                   PairState* __restrict__ state,
-                                                   PointPair32* __restrict__ pp, double inv_thr) {
+__global__ void __launch_bounds__(256) prep_norms(const PairDesc* __restrict__ desc,
+                                                  PairState* __restrict__ state) {
   const PairDesc d = desc[blockIdx.y];
   const int npp = (d.n + 1) >> 1;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,22 +93,12 @@ __global__ void __launch_bounds__(256) prep_points(const PairDesc* __restrict__ 
     const double2 b1 = reinterpret_cast<const double2*>(d.x1)[q];
     const double2 a2 = reinterpret_cast<const double2*>(d.x2)[p];
     const double2 b2 = reinterpret_cast<const double2*>(d.x2)[q];
-    PointPair32 o;
-    o.x1 = make_float2((float)a1.x, (float)b1.x);
-    o.y1 = make_float2((float)a1.y, (float)b1.y);
-    o.x2 = make_float2((float)a2.x, (float)b2.x);
-    o.y2 = make_float2((float)a2.y, (float)b2.y);
-    o.x2s = make_float2((float)(a2.x * inv_thr), (float)(b2.x * inv_thr));
-    o.y2s = make_float2((float)(a2.y * inv_thr), (float)(b2.y * inv_thr));
-    pp[d.pp_off + g] = o;
     const double s1a = a1.x * a1.x + a1.y * a1.y, s1b = b1.x * b1.x + b1.y * b1.y;
     const double s2a = a2.x * a2.x + a2.y * a2.y, s2b = b2.x * b2.x + b2.y * b2.y;
     // !(x < big) catches NaN and Inf as well (fmax alone would drop a NaN operand)
     bad = !(s1a < 1e30) || !(s1b < 1e30) || !(s2a < 1e30) || !(s2b < 1e30);
-    const double s1 = fmax(s1a, s1b) + 1.0;
-    const double s2 = fmax(s2a, s2b) + 1.0;
-    r1 = __double2float_ru(s1);
-    r2 = __double2float_ru(s2);
+    r1 = __double2float_ru(fmax(s1a, s1b) + 1.0);
+    r2 = __double2float_ru(fmax(s2a, s2b) + 1.0);
   }
   r1 = warp_max(bad ? 0.f : r1);
   r2 = warp_max(bad ? 0.f : r2);
@@ -121,24 +111,83 @@ __global__ void __launch_bounds__(256) prep_points(const PairDesc* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// band_consts: one thread per image pair.  Guard-band constants (DESIGN.md "guard band"):
+//   computed n' = num/thr has |error| <= Bn = 8.2 u R1 R2 / thr   (u = 2^-24, ||E^||_F = 1,
+//   R1 = max||(x1,1)||, R2 = max||(x2,1)||), sqrt(d) has |error| <= Bd = 18 u max(R1,R2).
+//   With B = 1.02 (Bn + Bd):  sure-in  <=  (|n'|+B)^2 <= d,  sure-out  <=  (|n'|-B)^2 > d, and
+//   2 B |n'| <= c n'^2 + B^2/c  gives the multiply-add forms used by eval_pair.
+// ------------------------------------------------------------------------------------------
+__global__ void band_consts(const PairDesc* __restrict__ desc, PairState* __restrict__ state, int B,
+                            double thr, int allow_fast) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  PairState& s = state[b];
+  const PairDesc& d = desc[b];
+  const double u = 5.9604644775390625e-8;
+  const double R1 = sqrt((double)__uint_as_float(s.r1_bits));
+  const double R2 = sqrt((double)__uint_as_float(s.r2_bits));
+  const double Bn = 8.2 * u * R1 * R2 / thr;
+  const double Bd = 18.0 * u * fmax(R1, R2);
+  const double Bt = 1.02 * (Bn + Bd);
+  const int fast = allow_fast && !s.nonfinite && d.n_pre == d.n_full && (R1 < 1024.0) &&
+                   (R2 < 1024.0) && (Bt < 0.125) && (Bt > 0.0);
+  double c = fmin(0.25, fmax(3.0 * Bt, 1.0 / 1024.0));
+  const double K = 1.02 * Bt * Bt * (1.0 + 1.0 / c);
+  c += 16.0 * u;  // covers the rounding of the final evaluations themselves
+  s.band.K = __double2float_ru(K);
+  s.band.ratio = __double2float_ru((1.0 + c) / (1.0 - c));
+  s.band.two_K = __double2float_ru(2.0 * K) * 1.000001f;
+  s.band.pad = 0.f;
+  s.s_scale = fast ? sqrt(1.0 - c) / thr : 1.0;
+  s.fast = fast;
+}
+
+// ------------------------------------------------------------------------------------------
+// prep_points: grid (ceil(max_pp / 256), B) — float32 point pairs for the scorer
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_points(const PairDesc* __restrict__ desc,
+                                                   const PairState* __restrict__ state,
+                                                   PointPair32* __restrict__ pp) {
+  const PairDesc d = desc[blockIdx.y];
+  if (!state[blockIdx.y].fast) return;
+  const double sc = state[blockIdx.y].s_scale;
+  const int npp = (d.n + 1) >> 1;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= npp) return;
+  const int p = 2 * g, q = min(2 * g + 1, d.n - 1);
+  const double2 a1 = reinterpret_cast<const double2*>(d.x1)[p];
+  const double2 b1 = reinterpret_cast<const double2*>(d.x1)[q];
+  const double2 a2 = reinterpret_cast<const double2*>(d.x2)[p];
+  const double2 b2 = reinterpret_cast<const double2*>(d.x2)[q];
+  PointPair32 o;
+  o.x1 = make_float2((float)a1.x, (float)b1.x);
+  o.y1 = make_float2((float)a1.y, (float)b1.y);
+  o.x2 = make_float2((float)a2.x, (float)b2.x);
+  o.y2 = make_float2((float)a2.y, (float)b2.y);
+  o.x2s = make_float2((float)(a2.x * sc), (float)(b2.x * sc));
+  o.y2s = make_float2((float)(a2.y * sc), (float)(b2.y * sc));
+  pp[d.pp_off + g] = o;
+}
+
+// ------------------------------------------------------------------------------------------
 // solve_sets: one thread per minimal set, grid (ceil(H/32), B), block 32
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void make_hyp32(const double* E, double inv_thr, Hyp32& h) {
+__device__ __forceinline__ void make_hyp32(const double* E, double sc, Hyp32& h) {
   double s = 0.0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) s += E[i] * E[i];
   const double f = 1.0 / sqrt(s);
   h.e00 = (float)(E[0] * f); h.e01 = (float)(E[1] * f); h.e02 = (float)(E[2] * f);
   h.e10 = (float)(E[3] * f); h.e11 = (float)(E[4] * f); h.e12 = (float)(E[5] * f);
-  h.g0 = (float)(E[6] * f * inv_thr); h.g1 = (float)(E[7] * f * inv_thr);
-  h.g2 = (float)(E[8] * f * inv_thr);
+  h.g0 = (float)(E[6] * f * sc); h.g1 = (float)(E[7] * f * sc);
+  h.g2 = (float)(E[8] * f * sc);
   h.e20 = (float)(E[6] * f); h.e21 = (float)(E[7] * f);
   h.pad = 0.f;
 }
 
 __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ desc,
                                                  PairState* __restrict__ state, int H,
-                                                 int with_cheirality, double inv_thr,
+                                                 int with_cheirality,
                                                  double* __restrict__ E_list,
                                                  double* __restrict__ P_list,
                                                  int32_t* __restrict__ n_valid,
@@ -171,9 +220,10 @@ __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ de
   if (hyp && nv > 0) {
     const int base = atomicAdd(&state[b].M, nv);
     const size_t o = (size_t)b * H * 10 + base;
+    const double sc = state[b].s_scale;
     for (int j = 0; j < nv; ++j) {
       Hyp32 r;
-      make_hyp32(E + 9 * j, inv_thr, r);
+      make_hyp32(E + 9 * j, sc, r);
       hyp[o + j] = r;
       hyp_id[o + j] = h * 16 + j;
       notin[o + j] = 0u;
@@ -183,14 +233,14 @@ __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ de
 }
 
 // float32 hypothesis records for an arbitrary E list (tv5_score_bounds)
-__global__ void hyps_from_list(const double* __restrict__ E_list, int M, double inv_thr,
-                               PairState* state, Hyp32* __restrict__ hyp, int32_t* hyp_id,
-                               uint32_t* notin, uint32_t* out) {
+__global__ void hyps_from_list(const double* __restrict__ E_list, int M, PairState* state,
+                               Hyp32* __restrict__ hyp, int32_t* hyp_id, uint32_t* notin,
+                               uint32_t* out) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m == 0) state[0].M = M;
   if (m >= M) return;
   Hyp32 r;
-  make_hyp32(E_list + 9 * (size_t)m, inv_thr, r);
+  make_hyp32(E_list + 9 * (size_t)m, state[0].s_scale, r);
   hyp[m] = r;
   hyp_id[m] = m;
   notin[m] = 0u;
@@ -198,49 +248,61 @@ __global__ void hyps_from_list(const double* __restrict__ E_list, int M, double 
 }
 
 // ------------------------------------------------------------------------------------------
-// plan_tiles: one CTA.  Guard-band constants (DESIGN.md "guard band") and the tile table.
-//   computed n' = num/thr has |error| <= Bn = 8.2 u R1 R2 / thr   (u = 2^-24, ||E^||_F = 1,
-//   R1 = max||(x1,1)||, R2 = max||(x2,1)||), sqrt(d) has |error| <= Bd = 18 u max(R1,R2).
-//   With B = 1.02 (Bn + Bd):  sure-in  <=  (|n'|+B)^2 <= d,  sure-out  <=  (|n'|-B)^2 > d, and
-//   2 B |n'| <= c n'^2 + B^2/c  gives the multiply-add form used by eval_pair.
+// plan_tiles: one CTA of 1024 threads; tile table = exclusive prefix sum of tiles per pair.
 // ------------------------------------------------------------------------------------------
-__global__ void plan_tiles(const PairDesc* __restrict__ desc, PairState* __restrict__ state,
-                           Control* __restrict__ ctl, int B, int pp_per_tile, double thr,
-                           int allow_fast) {
-  if (threadIdx.x != 0) return;
-  int total = 0;
-  for (int b = 0; b < B; ++b) {
-    PairState& s = state[b];
-    const PairDesc& d = desc[b];
-    const double u = 5.9604644775390625e-8;
-    const double R1 = sqrt((double)__uint_as_float(s.r1_bits));
-    const double R2 = sqrt((double)__uint_as_float(s.r2_bits));
-    const double Bn = 8.2 * u * R1 * R2 / thr;
-    const double Bd = 18.0 * u * fmax(R1, R2);
-    const double Bt = 1.02 * (Bn + Bd);
-    int fast = allow_fast && !s.nonfinite && d.n_pre == d.n_full && (R1 < 1024.0) &&
-               (R2 < 1024.0) && (Bt < 0.125) && (Bt > 0.0);
-    double c = fmin(0.25, fmax(3.0 * Bt, 1.0 / 1024.0));
-    const double K = 1.02 * Bt * Bt * (1.0 + 1.0 / c);
-    c += 16.0 * u;  // covers the rounding of the final lo/hi evaluations themselves
-    s.band.neg_one_plus_c = -(float)(1.0 + c);
-    s.band.neg_one_minus_c = -__double2float_rd(1.0 - c);
-    s.band.neg_K = -__double2float_ru(K);
-    s.band.two_K = __double2float_ru(2.0 * K) * 1.000001f;
-    s.fast = fast;
-    s.tile_start = total;
-    const int npp = (d.n_full + 1) >> 1;
-    s.n_hc = (s.M + kHypChunk - 1) / kHypChunk;
-    s.n_pc = (npp + pp_per_tile - 1) / pp_per_tile;
-    if (fast) total += s.n_hc * s.n_pc;
+__global__ void __launch_bounds__(1024) plan_tiles(const PairDesc* __restrict__ desc,
+                                                   PairState* __restrict__ state,
+                                                   Control* __restrict__ ctl, int B, int pp_per_tile) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+    const int b = b0 + threadIdx.x;
+    int tiles = 0;
+    if (b < B) {
+      PairState& s = state[b];
+      const int npp = (desc[b].n_full + 1) >> 1;
+      s.n_hc = (s.M + kHypChunk - 1) / kHypChunk;
+      s.n_pc = (npp + pp_per_tile - 1) / pp_per_tile;
+      tiles = s.fast ? s.n_hc * s.n_pc : 0;
+    }
+    // inclusive scan inside the warp, then across warps
+    int v = tiles;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) >= o) v += t;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = s_warp[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += t;
+      }
+      s_warp[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int warp_off = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
+    const int base = s_base;
+    if (b < B) state[b].tile_start = base + warp_off + v - tiles;
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = base + s_warp[31];
+    __syncthreads();
   }
-  ctl->n_tiles = total;
-  ctl->tile_counter = 0;
+  if (threadIdx.x == 0) {
+    ctl->n_tiles = s_base;
+    ctl->tile_counter = 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // score_bounds: persistent CTAs pulling (pair, hypothesis chunk, point chunk) tiles.
 // ------------------------------------------------------------------------------------------
+template <bool TWO_SIDED>
 __global__ void __launch_bounds__(kScoreThreads, 2)
 score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ state,
              Control* __restrict__ ctl, int B, int H, int pp_per_tile,
@@ -299,8 +361,7 @@ score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ st
       }
       load_hyp(hr[k], raw);
     }
-    const float2 nc1 = dup(s.band.neg_one_plus_c), nc2 = dup(s.band.neg_one_minus_c);
-    const float2 negK = dup(s.band.neg_K), twoK = dup(s.band.two_K);
+    const float2 bK = dup(s.band.K), nratio = dup(-s.band.ratio), ntwoK = dup(-s.band.two_K);
     uint32_t a[kHypPerThread], o[kHypPerThread];
 #pragma unroll
     for (int k = 0; k < kHypPerThread; ++k) { a[k] = 0u; o[k] = 0u; }
@@ -314,19 +375,19 @@ score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ st
     for (int i = 0; i < nfull; ++i) {
       const PointPair32 p = tile[i];
 #pragma unroll
-      for (int k = 0; k < kHypPerThread; ++k) eval_pair(hr[k], p, nc1, nc2, negK, twoK, a[k], o[k]);
+      for (int k = 0; k < kHypPerThread; ++k) eval_pair<TWO_SIDED>(hr[k], p, bK, nratio, ntwoK, a[k], o[k]);
     }
     if (odd_tail) {
       const PointPair32 p = tile[nfull];
 #pragma unroll
       for (int k = 0; k < kHypPerThread; ++k)
-        eval_pair(hr[k], p, nc1, nc2, negK, twoK, a[k], o[k], false);
+        eval_pair<TWO_SIDED>(hr[k], p, bK, nratio, ntwoK, a[k], o[k], false);
     }
 #pragma unroll
     for (int k = 0; k < kHypPerThread; ++k)
       if (live[k]) {
         const size_t slot = hbase + k * kScoreThreads + tid;
-        if (a[k]) atomicAdd(&notin[slot], a[k]);
+        if (TWO_SIDED && a[k]) atomicAdd(&notin[slot], a[k]);
         if (o[k]) atomicAdd(&out[slot], o[k]);
       }
     __syncthreads();  // everyone is done with `tile` and `s_tile` before the next round
@@ -334,39 +395,68 @@ score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ st
 }
 
 // ------------------------------------------------------------------------------------------
-// pick_candidates: one CTA per image pair
+// Candidate selection from the upper bounds hi[m] = n - out[m]  (exact count <= hi), one CTA per
+// image pair, two rounds:
+//   pick_top   the hypothesis with the largest hi (first by id)       -> exact count L
+//   pick_rest  every other hypothesis with hi >= max(L, 1)            -> exact counts
+// The true winner w has exact(w) >= L and hi(w) >= exact(w), so it is in the second set; ties
+// are all included, so the first-maximum rule can be applied exactly by `finalize`.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pick_candidates(const PairDesc* __restrict__ desc,
-                                                       PairState* __restrict__ state, int H,
-                                                       const uint32_t* __restrict__ notin,
-                                                       const uint32_t* __restrict__ out,
-                                                       int32_t* __restrict__ cand,
-                                                       int32_t* __restrict__ cand_cnt) {
+__global__ void __launch_bounds__(256) pick_top(const PairDesc* __restrict__ desc,
+                                                PairState* __restrict__ state, int H,
+                                                const uint32_t* __restrict__ out,
+                                                const int32_t* __restrict__ hyp_id,
+                                                int32_t* __restrict__ cand,
+                                                int32_t* __restrict__ cand_cnt) {
   const int b = blockIdx.x;
   PairState& s = state[b];
   const int M = s.M;
   const size_t base = (size_t)b * H * 10;
-  __shared__ int s_best[8];
-  __shared__ int s_L;
   if (!s.fast) {  // float64 path: every hypothesis is a candidate
     for (int m = threadIdx.x; m < M; m += blockDim.x) { cand[base + m] = m; cand_cnt[base + m] = 0; }
-    if (threadIdx.x == 0) s.n_cand = M;
+    if (threadIdx.x == 0) { s.n_cand = M; s.exact_from = 0; }
     return;
   }
+  __shared__ unsigned long long s_key[8];
   const int n = desc[b].n_full;
-  int best = 0;
-  for (int m = threadIdx.x; m < M; m += blockDim.x) best = max(best, n - (int)notin[base + m]);
-  best = warp_max(best);
-  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int L = 0;
-    for (int w = 0; w < 8; ++w) L = max(L, s_best[w]);
-    s_L = max(L, 1);  // a hypothesis that cannot have a single inlier never wins
-  }
-  __syncthreads();
-  const int L = s_L;
+  unsigned long long key = 0ull;  // (hi << 32 | ~id) << 0, slot recovered by a second pass
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const uint32_t hi = (uint32_t)(n - (int)out[base + m]);
+    const unsigned long long k = ((unsigned long long)hi << 32) | (0xFFFFFFFFu - (uint32_t)hyp_id[base + m]);
+    key = k > key ? k : key;
+  }
+  key = warp_max(key);
+  if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
+  __syncthreads();
+  unsigned long long best = 0ull;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) best = s_key[w] > best ? s_key[w] : best;
+  const int best_id = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
+  if (threadIdx.x == 0) { s.n_cand = M > 0 ? 1 : 0; s.exact_from = 0; }
+  for (int m = threadIdx.x; m < M; m += blockDim.x)
+    if (hyp_id[base + m] == best_id) { cand[base] = m; cand_cnt[base] = 0; }
+}
+
+__global__ void __launch_bounds__(256) pick_rest(const PairDesc* __restrict__ desc,
+                                                 PairState* __restrict__ state, int H,
+                                                 const uint32_t* __restrict__ out,
+                                                 int32_t* __restrict__ cand,
+                                                 int32_t* __restrict__ cand_cnt) {
+  const int b = blockIdx.x;
+  PairState& s = state[b];
+  const size_t base = (size_t)b * H * 10;
+  if (!s.fast || s.M == 0) {
+    if (threadIdx.x == 0) s.exact_from = s.n_cand;  // nothing left to re-score
+    return;
+  }
+  const int M = s.M;
+  const int n = desc[b].n_full;
+  const int top = cand[base];
+  const int L = max(cand_cnt[base], 1);  // a hypothesis that cannot have a single inlier never wins
+  __syncthreads();
+  if (threadIdx.x == 0) s.exact_from = 1;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    if (m == top) continue;
     const int hi = n - (int)out[base + m];
     if (hi >= L) {
       const int i = atomicAdd(&s.n_cand, 1);
@@ -388,13 +478,14 @@ __global__ void __launch_bounds__(256) exact_counts(const PairDesc* __restrict__
                                                     int32_t* __restrict__ cand_cnt) {
   const int b = blockIdx.y;
   const PairDesc d = desc[b];
-  const int n_cand = state[b].n_cand;
+  const int first = state[b].exact_from;
+  const int n_cand = state[b].n_cand - first;
   const int n = d.n_full;
   const int n_chunks = (n + kExactChunk - 1) / kExactChunk;
   const size_t base = (size_t)b * H * 10;
   __shared__ int s_part[8];
   for (int item = blockIdx.x; item < n_cand * n_chunks; item += gridDim.x) {
-    const int ci = item / n_chunks, ch = item - ci * n_chunks;
+    const int ci = first + item / n_chunks, ch = item % n_chunks;
     const int id = hyp_id[base + cand[base + ci]];
     const double* Eg = E_list + ((size_t)b * H + (id >> 4)) * 90 + (id & 15) * 9;
     double E[9];
@@ -519,7 +610,7 @@ __global__ void __launch_bounds__(256) set_winners(PairDesc* __restrict__ desc,
     scratch[sbase + m] = win ? 1 : 0;
   }
   __syncthreads();
-  if (threadIdx.x == 0) s.n_cand = 0;
+  if (threadIdx.x == 0) { s.n_cand = 0; s.exact_from = 0; }
   __syncthreads();
   for (int m = threadIdx.x; m < M; m += blockDim.x)
     if (scratch[sbase + m]) {
@@ -774,6 +865,11 @@ int tv5_destroy(tv5_ctx* ctx) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& t : ctx->rng_tables) cudaFree(t.sets);
+  if (ctx->copy_stream) {
+    cudaStreamDestroy(ctx->copy_stream);
+    for (auto& e : ctx->chunk_ev) cudaEventDestroy(e);
+    cudaEventDestroy(ctx->start_ev);
+  }
   for (int i = 0; i <= TV5_N_STAGES; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   delete ctx;
@@ -860,15 +956,16 @@ int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, 
   Workspace& w = ctx->ws;
   TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, hd.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, st));
   TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState) * B, st));
-  const double inv_thr = 1.0 / thr;
+  const int allow_fast = (two_stage || ctx->force_exact) ? 0 : 1;
 
   stage_mark(ctx, st, 0);
-  prep_points<<<dim3((max_pp + 255) / 256, B), 256, 0, st>>>(w.desc, w.state, w.pp, inv_thr);
+  prep_norms<<<dim3((max_pp + 255) / 256, B), 256, 0, st>>>(w.desc, w.state);
+  band_consts<<<(B + 127) / 128, 128, 0, st>>>(w.desc, w.state, B, thr, allow_fast);
+  if (allow_fast) prep_points<<<dim3((max_pp + 255) / 256, B), 256, 0, st>>>(w.desc, w.state, w.pp);
   stage_mark(ctx, st, 1);
-  solve_sets<<<dim3((H + 31) / 32, B), 32, 0, st>>>(w.desc, w.state, H, with_cheirality, inv_thr,
-                                                   w.E_list, with_cheirality ? w.P_list : nullptr,
-                                                   w.n_valid, w.n_roots, w.hyp, w.hyp_id, w.notin,
-                                                   w.out);
+  solve_sets<<<dim3((H + 31) / 32, B), 32, 0, st>>>(w.desc, w.state, H, with_cheirality, w.E_list,
+                                                   with_cheirality ? w.P_list : nullptr, w.n_valid,
+                                                   w.n_roots, w.hyp, w.hyp_id, w.notin, w.out);
   stage_mark(ctx, st, 2);
   // tile size: big tiles for batches, enough tiles to balance 2 CTAs/SM for a single pair
   const int slots = 2 * ctx->sm_count;
@@ -883,27 +980,31 @@ int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, 
       pp_per_tile = std::max(64, std::min(kMaxTilePairs, t));
     }
   }
-  plan_tiles<<<1, 32, 0, st>>>(w.desc, w.state, w.ctl, B, pp_per_tile, thr, (two_stage || ctx->force_exact) ? 0 : 1);
+  plan_tiles<<<1, 1024, 0, st>>>(w.desc, w.state, w.ctl, B, pp_per_tile);
   stage_mark(ctx, st, 3);
-  if (!two_stage) {
-    const int grid = slots;
-    score_bounds<<<grid, kScoreThreads, 0, st>>>(w.desc, w.state, w.ctl, B, H, pp_per_tile, w.pp,
-                                                 w.hyp, w.notin, w.out);
-  }
+  if (allow_fast)
+    score_bounds<false><<<slots, kScoreThreads, 0, st>>>(w.desc, w.state, w.ctl, B, H, pp_per_tile, w.pp,
+                                                         w.hyp, w.notin, w.out);
   stage_mark(ctx, st, 4);
-  pick_candidates<<<B, 256, 0, st>>>(w.desc, w.state, H, w.notin, w.out, w.cand, w.cand_cnt);
   const int X = std::max(1, std::min(4096, (4 * ctx->sm_count + B - 1) / B));
+  pick_top<<<B, 256, 0, st>>>(w.desc, w.state, H, w.out, w.hyp_id, w.cand, w.cand_cnt);
   if (two_stage) {
-    // stage A runs on n_pre points: exact_counts reads n_full, so descriptors are swapped on
-    // the device between the two stages by re-uploading them.
+    // stage A runs on n_pre points: exact_counts reads n_full, so the descriptors are
+    // re-uploaded with n_full := n_pre for this stage and restored afterwards.
     std::vector<PairDesc> ha = hd;
     for (auto& d : ha) d.n_full = d.n_pre;
     TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, ha.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, st));
     exact_counts<<<dim3(X, B), 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, w.hyp_id, w.cand, w.cand_cnt);
     set_winners<<<B, 256, 0, st>>>(w.desc, w.state, H, w.hyp_id, w.cand, w.cand_cnt, w.cand + w.sets_cap * 10);
     TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, hd.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, st));
+    exact_counts<<<dim3(X, B), 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, w.hyp_id, w.cand, w.cand_cnt);
+  } else {
+    exact_counts<<<dim3(X, B), 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, w.hyp_id, w.cand, w.cand_cnt);
+    if (allow_fast) {
+      pick_rest<<<B, 256, 0, st>>>(w.desc, w.state, H, w.out, w.cand, w.cand_cnt);
+      exact_counts<<<dim3(X, B), 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, w.hyp_id, w.cand, w.cand_cnt);
+    }
   }
-  exact_counts<<<dim3(X, B), 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, w.hyp_id, w.cand, w.cand_cnt);
   stage_mark(ctx, st, 5);
   finalize<<<B, 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, with_cheirality ? w.P_list : nullptr,
                               w.hyp_id, w.cand, w.cand_cnt);
@@ -942,17 +1043,46 @@ int tv5_compute_pose_batch_host(tv5_ctx* ctx, void* stream, int B, const double*
     if ((rc = grow_same(ctx, w.out_res, w.out_cap, (size_t)B))) return rc;
     w.out_cap = (size_t)B;
   }
+  if (!ctx->copy_stream) {
+    TV5_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->chunk_ev) TV5_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    TV5_CUDA(ctx, cudaEventCreateWithFlags(&ctx->start_ev, cudaEventDisableTiming));
+  }
+  // Pipeline: the batch is cut into up to kHostChunks chunks of pairs; the host->device copies of
+  // chunk k+1 (own stream) overlap the kernels of chunk k (caller's stream).
+  const int n_chunks = std::min(kHostChunks, B);
   double* dx1 = w.h2d_x;
   double* dx2 = w.h2d_x + total * 2;
-  TV5_CUDA(ctx, cudaMemcpyAsync(dx1, x1 + 2 * pt_offsets[0], total * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-  TV5_CUDA(ctx, cudaMemcpyAsync(dx2, x2 + 2 * pt_offsets[0], total * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (sets)
-    TV5_CUDA(ctx, cudaMemcpyAsync(w.h2d_sets, sets, (size_t)B * H * 5 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  std::vector<int64_t> off((size_t)B + 1);
-  for (int b = 0; b <= B; ++b) off[b] = pt_offsets[b] - pt_offsets[0];
-  rc = tv5_compute_pose_batch(ctx, stream, B, dx1, dx2, off.data(), sets ? w.h2d_sets : nullptr, iters,
-                              n_pre, n_full, thr, with_cheirality, w.out_E, w.out_P, w.out_res, nullptr);
-  if (rc) return rc;
+  TV5_CUDA(ctx, cudaEventRecord(ctx->start_ev, st));
+  TV5_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->start_ev, 0));
+  std::vector<int> first(n_chunks + 1);
+  for (int k = 0; k <= n_chunks; ++k) first[k] = (int)((int64_t)B * k / n_chunks);
+  for (int k = 0; k < n_chunks; ++k) {
+    const int b0 = first[k], b1 = first[k + 1];
+    const size_t p0 = (size_t)(pt_offsets[b0] - pt_offsets[0]), np = (size_t)(pt_offsets[b1] - pt_offsets[b0]);
+    TV5_CUDA(ctx, cudaMemcpyAsync(dx1 + 2 * p0, x1 + 2 * pt_offsets[b0], np * 2 * sizeof(double),
+                                  cudaMemcpyHostToDevice, ctx->copy_stream));
+    TV5_CUDA(ctx, cudaMemcpyAsync(dx2 + 2 * p0, x2 + 2 * pt_offsets[b0], np * 2 * sizeof(double),
+                                  cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (sets)
+      TV5_CUDA(ctx, cudaMemcpyAsync(w.h2d_sets + (size_t)b0 * H * 5, sets + (size_t)b0 * H * 5,
+                                    (size_t)(b1 - b0) * H * 5 * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                    ctx->copy_stream));
+    TV5_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[k], ctx->copy_stream));
+  }
+  std::vector<int64_t> off;
+  for (int k = 0; k < n_chunks; ++k) {
+    const int b0 = first[k], b1 = first[k + 1];
+    off.assign((size_t)(b1 - b0) + 1, 0);
+    for (int b = b0; b <= b1; ++b) off[b - b0] = pt_offsets[b] - pt_offsets[b0];
+    const size_t p0 = (size_t)(pt_offsets[b0] - pt_offsets[0]);
+    TV5_CUDA(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
+    rc = tv5_compute_pose_batch(ctx, stream, b1 - b0, dx1 + 2 * p0, dx2 + 2 * p0, off.data(),
+                                sets ? w.h2d_sets + (size_t)b0 * H * 5 : nullptr, iters, n_pre, n_full, thr,
+                                with_cheirality, w.out_E + 9 * (size_t)b0, w.out_P + 12 * (size_t)b0,
+                                w.out_res + b0, nullptr);
+    if (rc) return rc;
+  }
   TV5_CUDA(ctx, cudaMemcpyAsync(E_out, w.out_E, (size_t)B * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (P_out) TV5_CUDA(ctx, cudaMemcpyAsync(P_out, w.out_P, (size_t)B * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TV5_CUDA(ctx, cudaMemcpyAsync(result, w.out_res, (size_t)B * sizeof(tv5_result), cudaMemcpyDeviceToHost, st));
@@ -974,7 +1104,7 @@ int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, i
   TV5_CUDA(ctx, cudaMemcpyAsync(ctx->ws.desc, &d, sizeof(d), cudaMemcpyHostToDevice, st));
   TV5_CUDA(ctx, cudaMemsetAsync(E_list, 0, (size_t)H * 90 * sizeof(double), st));
   if (P_list) TV5_CUDA(ctx, cudaMemsetAsync(P_list, 0, (size_t)H * 120 * sizeof(double), st));
-  solve_sets<<<dim3((H + 31) / 32, 1), 32, 0, st>>>(ctx->ws.desc, ctx->ws.state, H, with_cheirality, 1.0,
+  solve_sets<<<dim3((H + 31) / 32, 1), 32, 0, st>>>(ctx->ws.desc, ctx->ws.state, H, with_cheirality,
                                                    E_list, with_cheirality ? P_list : nullptr, n_valid,
                                                    n_roots, nullptr, nullptr, nullptr, nullptr);
   TV5_CUDA(ctx, cudaGetLastError());
@@ -1015,12 +1145,13 @@ int tv5_score_bounds(tv5_ctx* ctx, void* stream, const double* x1, const double*
   d.x1 = x1; d.x2 = x2; d.n = n_test; d.n_pre = d.n_full = n_test; d.pp_off = 0;
   TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, &d, sizeof(d), cudaMemcpyHostToDevice, st));
   TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState), st));
-  const double inv_thr = 1.0 / thr;
   const int npp = (n_test + 1) / 2;
   stage_mark(ctx, st, 0);
-  prep_points<<<dim3((npp + 255) / 256, 1), 256, 0, st>>>(w.desc, w.state, w.pp, inv_thr);
+  prep_norms<<<dim3((npp + 255) / 256, 1), 256, 0, st>>>(w.desc, w.state);
+  band_consts<<<1, 32, 0, st>>>(w.desc, w.state, 1, thr, 1);
+  prep_points<<<dim3((npp + 255) / 256, 1), 256, 0, st>>>(w.desc, w.state, w.pp);
   stage_mark(ctx, st, 1);
-  hyps_from_list<<<(M + 255) / 256, 256, 0, st>>>(E_list, M, inv_thr, w.state, w.hyp, w.hyp_id, w.notin, w.out);
+  hyps_from_list<<<(M + 255) / 256, 256, 0, st>>>(E_list, M, w.state, w.hyp, w.hyp_id, w.notin, w.out);
   stage_mark(ctx, st, 2);
   const int slots = 2 * ctx->sm_count;
   int pp_per_tile = kMaxTilePairs;
@@ -1033,11 +1164,11 @@ int tv5_score_bounds(tv5_ctx* ctx, void* stream, const double* x1, const double*
       pp_per_tile = std::max(64, std::min(kMaxTilePairs, t));
     }
   }
-  plan_tiles<<<1, 32, 0, st>>>(w.desc, w.state, w.ctl, 1, pp_per_tile, thr, 1);
+  plan_tiles<<<1, 1024, 0, st>>>(w.desc, w.state, w.ctl, 1, pp_per_tile);
   stage_mark(ctx, st, 3);
   // H*10 is the stride between pairs inside the kernel; with one pair it is irrelevant
-  score_bounds<<<slots, kScoreThreads, 0, st>>>(w.desc, w.state, w.ctl, 1, H, pp_per_tile, w.pp, w.hyp,
-                                               w.notin, w.out);
+  score_bounds<true><<<slots, kScoreThreads, 0, st>>>(w.desc, w.state, w.ctl, 1, H, pp_per_tile, w.pp, w.hyp,
+                                                      w.notin, w.out);
   stage_mark(ctx, st, 4);
   bounds_to_lo_hi<<<(M + 255) / 256, 256, 0, st>>>(w.notin, w.out, M, n_test, lo, hi);
   stage_mark(ctx, st, 5);

@@ -8,13 +8,18 @@
 #include "../../include/tv5.h"
 #include "score.cuh"
 
+#ifndef TV5_HYP_PER_THREAD
+#define TV5_HYP_PER_THREAD 4
+#endif
+
 namespace tv5 {
 
 constexpr int kScoreThreads = 256;   // threads per scoring CTA
-constexpr int kHypPerThread = 2;     // hypotheses held in registers per thread
+constexpr int kHypPerThread = TV5_HYP_PER_THREAD;  // hypotheses held in registers per thread
 constexpr int kHypChunk = kScoreThreads * kHypPerThread;
 constexpr int kMaxTilePairs = 512;   // point pairs staged in shared memory per tile (24 KB)
 constexpr int kExactChunk = 2048;    // points per work item of the float64 scorer
+constexpr int kHostChunks = 8;       // pipeline depth of the host-buffer entry point
 
 // Per image pair: geometry of the job (written by the host) ...
 struct PairDesc {
@@ -40,7 +45,8 @@ struct PairState {
   int32_t tile_start;     // first scoring tile of this pair
   int32_t n_hc, n_pc;     // tiles = hypothesis chunks x point chunks
   int32_t n_cand;         // hypotheses to re-score exactly (atomic)
-  int32_t pad;
+  int32_t exact_from;     // first candidate not yet re-scored
+  double s_scale;         // sqrt(1-c)/thr folded into the float32 point / hypothesis records
   BandConst band;
 };
 
@@ -89,4 +95,7 @@ struct tv5_ctx {
   double stage_ms[TV5_N_STAGES] = {};
   int64_t stage_launches[TV5_N_STAGES] = {};
   bool ev_pending = false;
+  cudaStream_t copy_stream = nullptr;   // host-buffer entry point: H2D copies overlap compute
+  cudaEvent_t chunk_ev[tv5::kHostChunks] = {};
+  cudaEvent_t start_ev = nullptr;
 };

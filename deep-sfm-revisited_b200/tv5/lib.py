@@ -6,7 +6,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _REPO = os.path.dirname(_PKG)
-_SO = os.path.join(_PKG, "libtv5.so")
+_SO = os.environ.get("TV5_LIB") or os.path.join(_PKG, "libtv5.so")  # TV5_LIB: dev builds only
 _HEADER = os.path.join(_REPO, "include", "tv5.h")
 
 TV5_N_STAGES = 6

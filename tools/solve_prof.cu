@@ -5,7 +5,7 @@
 #include <random>
 #include "../deep-sfm-revisited_b200/csrc/solve5.cuh"
 using namespace tv5;
-__global__ void k(const double* x1, const double* x2, const int* sets, int H, double* E, double* P, int* nv) {
+__global__ void __launch_bounds__(32, MINB) k(const double* x1, const double* x2, const int* sets, int H, double* E, double* P, int* nv) {
   int h = blockIdx.x * blockDim.x + threadIdx.x; if (h >= H) return;
   double q[5][2], qp[5][2];
   for (int i = 0; i < 5; ++i) { int idx = sets[5*h+i]; q[i][0]=x1[2*idx]; q[i][1]=x1[2*idx+1]; qp[i][0]=x2[2*idx]; qp[i][1]=x2[2*idx+1]; }
