@@ -27,7 +27,7 @@
 namespace tv5 {
 
 #ifdef TV5_SOLVE_PROFILE
-__device__ unsigned long long g_solve_prof[8];
+__device__ unsigned long long g_solve_prof[16];
 #endif
 
 // Completion rows of the 9x9 system (filled by tv5_create from the recurrence
@@ -575,11 +575,17 @@ __device__ __forceinline__ double fast_refine(const FastChain& s, double lo, dou
     }
     if ((flo < 0.0) == (fhi < 0.0)) return 0.5 * (lo + hi);
   }
+#ifdef TV5_SOLVE_COUNT
+  atomicAdd(&g_solve_prof[11], 1ull);
+#endif
   // bracketed Newton (bisect when Newton leaves the bracket or converges too slowly)
   double xl = flo < 0.0 ? lo : hi, xh = flo < 0.0 ? hi : lo;
   double x = 0.5 * (lo + hi), dxold = fabs(hi - lo), dx = dxold, f, df;
   eval_p_dp(p, x, f, df);
   for (int it = 0; it < 64; ++it) {
+#ifdef TV5_SOLVE_COUNT
+    atomicAdd(&g_solve_prof[10], 1ull);
+#endif
     const bool bisect = (((x - xh) * df - f) * ((x - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df));
     dxold = dx;
     if (bisect) { dx = 0.5 * (xh - xl); x = xl + dx; } else { dx = f / df; x -= dx; }
@@ -633,6 +639,9 @@ __device__ inline int real_roots_deg10(const double (&poly)[11], double (&roots)
   slo[0] = -bound; shi[0] = bound; svlo[0] = vlo0; svhi[0] = vhi0;
   int nr = 0;
   for (int trip = 0; trip < 400 && sp > 0; ++trip) {
+#ifdef TV5_SOLVE_COUNT
+    atomicAdd(&g_solve_prof[8], 1ull);
+#endif
     const int t = sp - 1;
     const int n = svlo[t] - svhi[t];
     if (n <= 0) { --sp; continue; }
@@ -648,6 +657,9 @@ __device__ inline int real_roots_deg10(const double (&poly)[11], double (&roots)
       --sp;
       continue;
     }
+#ifdef TV5_SOLVE_COUNT
+    atomicAdd(&g_solve_prof[9], 1ull);
+#endif
     const int vmid = fast_changes(s, mid);
     const int n1 = svlo[t] - vmid, n2 = vmid - svhi[t];
     if (n1 > 0 && n2 > 0 && sp < 12) {   // split: right half below, left half on top (popped first)

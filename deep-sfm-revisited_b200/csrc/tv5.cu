@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "solve5.cuh"
+#include "solve5_coop.cuh"
 #include "tv5_internal.h"
 
 namespace tv5 {
@@ -196,8 +197,13 @@ __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ de
                                                  int32_t* __restrict__ hyp_id,
                                                  uint32_t* __restrict__ notin,
                                                  uint32_t* __restrict__ out) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= H) return;
+  __shared__ double sB[kCoopBasisDoubles][kCoopStride];
+  __shared__ double sR[kCoopRowsDoubles][kCoopStride];
+  __shared__ double sQ[kCoopPointDoubles][kCoopStride];
+  __shared__ int sOk[32];
+  const int h_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = h_raw < H;        // every lane takes part in the cooperative phase
+  const int h = valid ? h_raw : H - 1;
   const int b = blockIdx.y;
   const PairDesc d = desc[b];
   double q[5][2], qp[5][2];
@@ -214,7 +220,8 @@ __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ de
   double* E = E_list + s * 90;
   double* P = P_list ? P_list + s * 120 : nullptr;
   int nr = 0;
-  const int nv = solve_minimal_set(q, qp, with_cheirality != 0, E, P, &nr);
+  const int nv = solve_minimal_set_coop(valid, q, qp, with_cheirality != 0, E, P, &nr, sB, sR, sQ, sOk);
+  if (!valid) return;
   n_valid[s] = nv;
   if (n_roots) n_roots[s] = nr;
   if (hyp && nv > 0) {
@@ -303,7 +310,7 @@ __global__ void __launch_bounds__(1024) plan_tiles(const PairDesc* __restrict__ 
 // score_bounds: persistent CTAs pulling (pair, hypothesis chunk, point chunk) tiles.
 // ------------------------------------------------------------------------------------------
 template <bool TWO_SIDED>
-__global__ void __launch_bounds__(kScoreThreads, 2)
+__global__ void __launch_bounds__(kScoreThreads, TV5_SCORE_MINB)
 score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ state,
              Control* __restrict__ ctl, int B, int H, int pp_per_tile,
              const PointPair32* __restrict__ pp, const Hyp32* __restrict__ hyp,
@@ -371,7 +378,7 @@ score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ st
     // the very last point pair of an odd-sized image pair holds a duplicated point in lane .y
     const bool odd_tail = (pp0 + npp == npp_all) && (d.n_full & 1);
     const int nfull = odd_tail ? npp - 1 : npp;
-#pragma unroll 2
+#pragma unroll kScoreUnroll
     for (int i = 0; i < nfull; ++i) {
       const PointPair32 p = tile[i];
 #pragma unroll
@@ -968,7 +975,7 @@ int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, 
                                                    w.n_roots, w.hyp, w.hyp_id, w.notin, w.out);
   stage_mark(ctx, st, 2);
   // tile size: big tiles for batches, enough tiles to balance 2 CTAs/SM for a single pair
-  const int slots = 2 * ctx->sm_count;
+  const int slots = TV5_SCORE_MINB * ctx->sm_count;
   int pp_per_tile = kMaxTilePairs;
   {
     const double est_M = (double)H * (with_cheirality ? 3.0 : 4.5);
@@ -1153,7 +1160,7 @@ int tv5_score_bounds(tv5_ctx* ctx, void* stream, const double* x1, const double*
   stage_mark(ctx, st, 1);
   hyps_from_list<<<(M + 255) / 256, 256, 0, st>>>(E_list, M, w.state, w.hyp, w.hyp_id, w.notin, w.out);
   stage_mark(ctx, st, 2);
-  const int slots = 2 * ctx->sm_count;
+  const int slots = TV5_SCORE_MINB * ctx->sm_count;
   int pp_per_tile = kMaxTilePairs;
   {
     const double n_hc = std::max(1.0, (double)M / kHypChunk);

@@ -11,12 +11,21 @@
 #ifndef TV5_HYP_PER_THREAD
 #define TV5_HYP_PER_THREAD 4
 #endif
+#ifndef TV5_SCORE_MINB
+#define TV5_SCORE_MINB 2     // resident scoring CTAs per SM
+#endif
+#ifndef TV5_SCORE_UNROLL
+#define TV5_SCORE_UNROLL 2   // point pairs per loop trip
+#endif
+
+
 
 namespace tv5 {
 
 constexpr int kScoreThreads = 256;   // threads per scoring CTA
 constexpr int kHypPerThread = TV5_HYP_PER_THREAD;  // hypotheses held in registers per thread
 constexpr int kHypChunk = kScoreThreads * kHypPerThread;
+constexpr int kScoreUnroll = TV5_SCORE_UNROLL;
 constexpr int kMaxTilePairs = 512;   // point pairs staged in shared memory per tile (24 KB)
 constexpr int kExactChunk = 2048;    // points per work item of the float64 scorer
 constexpr int kHostChunks = 8;       // pipeline depth of the host-buffer entry point
