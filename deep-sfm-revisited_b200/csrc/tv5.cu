@@ -23,6 +23,7 @@
 
 #include "solve5.cuh"
 #include "solve5_coop.cuh"
+#include "polish.cuh"
 #include "tv5_internal.h"
 
 namespace tv5 {
@@ -868,7 +869,8 @@ int tv5_destroy(tv5_ctx* ctx) {
   Workspace& w = ctx->ws;
   void* ptrs[] = {w.desc, w.state, w.ctl, w.pp, w.E_list, w.P_list, w.n_valid, w.n_roots, w.hyp,
                   w.hyp_id, w.notin, w.out, w.cand, w.cand_cnt, w.h2d_x, w.h2d_sets, w.out_E,
-                  w.out_P, w.out_res};
+                  w.out_P, w.out_res, w.polish_jobs, w.polish_partial, w.polish_barrier,
+                  w.polish_x, w.polish_E};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& t : ctx->rng_tables) cudaFree(t.sets);
@@ -1187,6 +1189,118 @@ int tv5_score_bounds(tv5_ctx* ctx, void* stream, const double* x1, const double*
   TV5_CUDA(ctx, cudaMemcpyAsync(&hs, w.state, sizeof(hs), cudaMemcpyDeviceToHost, st));
   TV5_CUDA(ctx, cudaStreamSynchronize(st));
   return hs.fast ? TV5_OK : TV5_ERR_INVALID;
+}
+
+// ------------------------------------------------------------------------------------------
+// decomposition and refinement (polish.cuh)
+// ------------------------------------------------------------------------------------------
+int tv5_decompose(const double* E, double* angles) {
+  if (!E || !angles) return TV5_ERR_INVALID;
+  givens_to_angles(givens_decompose(E), angles);
+  return TV5_OK;
+}
+
+int tv5_decompose_uv(const double* E, double* U, double* V) {
+  if (!E || !U || !V) return TV5_ERR_INVALID;
+  givens_to_uv(givens_decompose(E), U, V);
+  return TV5_OK;
+}
+
+int tv5_decompose_batch(tv5_ctx* ctx, void* stream, const double* E, int B, double* angles, double* U,
+                        double* V) {
+  if (!ctx || !E || B < 0 || (!angles && !U && !V)) return TV5_ERR_INVALID;
+  if (B == 0) return TV5_OK;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  decompose_batch<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(E, B, angles, U, V);
+  TV5_CUDA(ctx, cudaGetLastError());
+  return TV5_OK;
+}
+
+int tv5_optimise_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, const double* x2,
+                       const int64_t* pt_offsets, const uint8_t* mask, double* E_io, double delta,
+                       double alpha, int max_reps, int32_t* iters_out) {
+  if (!ctx || B < 1 || !pt_offsets || !E_io || max_reps < 0) return TV5_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->polish_max_ctas) {
+    int per_sm = 0;
+    TV5_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, irls_polish, kPolishThreads, 0));
+    ctx->polish_max_ctas = std::max(1, per_sm) * ctx->sm_count;
+  }
+  Workspace& w = ctx->ws;
+  int rc;
+  // jobs go out in waves of at most polish_max_ctas CTAs (a cooperative launch must be co-resident)
+  for (int b0 = 0; b0 < B;) {
+    const int nb = std::min(B - b0, ctx->polish_max_ctas);
+    int64_t max_n = 0;
+    for (int b = b0; b < b0 + nb; ++b) {
+      const int64_t n = pt_offsets[b + 1] - pt_offsets[b];
+      if (n < 0 || n > 0x3fffffff || (n > 0 && (!x1 || !x2))) return TV5_ERR_INVALID;
+      max_n = std::max(max_n, n);
+    }
+    // about four points per thread, never more CTAs than fit
+    int G = (int)std::min<int64_t>((max_n + 4 * kPolishThreads - 1) / (4 * kPolishThreads),
+                                   (int64_t)(ctx->polish_max_ctas / nb));
+    G = std::max(G, 1);
+    PolishJob* jobs = (PolishJob*)w.polish_jobs;
+    if ((size_t)nb > w.polish_jobs_cap || !jobs) {
+      if ((rc = grow_same(ctx, jobs, w.polish_jobs_cap, (size_t)nb))) { w.polish_jobs = nullptr; w.polish_jobs_cap = 0; return rc; }
+      w.polish_jobs = jobs;
+      if ((rc = grow_same(ctx, w.polish_barrier, w.polish_jobs_cap, (size_t)nb))) return rc;
+      w.polish_jobs_cap = (size_t)nb;
+    }
+    if ((rc = grow(ctx, w.polish_partial, w.polish_partial_cap, (size_t)nb * 2 * G * kPolishTerms))) return rc;
+    std::vector<PolishJob> hj((size_t)nb);
+    for (int b = 0; b < nb; ++b) {
+      const int64_t o = pt_offsets[b0 + b];
+      hj[b].x1 = x1 + 2 * o;
+      hj[b].x2 = x2 + 2 * o;
+      hj[b].mask = mask ? mask + o : nullptr;
+      hj[b].E = E_io + 9 * (size_t)(b0 + b);
+      hj[b].iters_out = iters_out ? iters_out + b0 + b : nullptr;
+      hj[b].n = (int32_t)(pt_offsets[b0 + b + 1] - o);
+      hj[b].pad = 0;
+    }
+    TV5_CUDA(ctx, cudaMemcpyAsync(jobs, hj.data(), sizeof(PolishJob) * nb, cudaMemcpyHostToDevice, st));
+    TV5_CUDA(ctx, cudaMemsetAsync(w.polish_barrier, 0, sizeof(unsigned int) * nb, st));
+    const PolishJob* jp = jobs;
+    double* pp = w.polish_partial;
+    unsigned int* bp = w.polish_barrier;
+    void* args[] = {(void*)&jp, (void*)&G, (void*)&delta, (void*)&alpha, (void*)&max_reps, (void*)&pp, (void*)&bp};
+    TV5_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)irls_polish, dim3(nb * G), dim3(kPolishThreads), args, 0, st));
+    b0 += nb;
+  }
+  return TV5_OK;
+}
+
+int tv5_optimise(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
+                 const uint8_t* mask, double* E_io, double delta, double alpha, int max_reps,
+                 int32_t* iters_out) {
+  if (N < 0) return TV5_ERR_INVALID;
+  const int64_t off[2] = {0, N};
+  return tv5_optimise_batch(ctx, stream, 1, x1, x2, off, mask, E_io, delta, alpha, max_reps, iters_out);
+}
+
+int tv5_optimise_host(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
+                      const double* E_init, double delta, double alpha, int max_reps, double* E_out) {
+  if (!ctx || N < 0 || !E_init || !E_out || (N > 0 && (!x1 || !x2))) return TV5_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  Workspace& w = ctx->ws;
+  int rc;
+  if ((rc = grow(ctx, w.polish_x, w.polish_x_cap, (size_t)std::max(N, 1) * 4))) return rc;
+  if (!w.polish_E && cudaMalloc(&w.polish_E, 9 * sizeof(double)) != cudaSuccess) return TV5_ERR_NOMEM;
+  if (N > 0) {
+    TV5_CUDA(ctx, cudaMemcpyAsync(w.polish_x, x1, (size_t)N * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    TV5_CUDA(ctx, cudaMemcpyAsync(w.polish_x + 2 * (size_t)N, x2, (size_t)N * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  TV5_CUDA(ctx, cudaMemcpyAsync(w.polish_E, E_init, 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+  rc = tv5_optimise(ctx, stream, w.polish_x, w.polish_x + 2 * (size_t)N, N, nullptr, w.polish_E, delta, alpha,
+                    max_reps, nullptr);
+  if (rc) return rc;
+  TV5_CUDA(ctx, cudaMemcpyAsync(E_out, w.polish_E, 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TV5_CUDA(ctx, cudaStreamSynchronize(st));
+  return TV5_OK;
 }
 
 int tv5_measure_fp32_peak(tv5_ctx* ctx, int mode, double* tflops_out) {

@@ -86,6 +86,12 @@ struct Workspace {
   double* out_E = nullptr;   size_t out_cap = 0;      // [B*9], [B*12], results
   double* out_P = nullptr;
   tv5_result* out_res = nullptr;
+  // refinement (polish.cuh): job table, per-CTA partial sums, per-job barrier counters
+  void* polish_jobs = nullptr; size_t polish_jobs_cap = 0;     // [jobs] PolishJob
+  double* polish_partial = nullptr; size_t polish_partial_cap = 0;
+  unsigned int* polish_barrier = nullptr;
+  double* polish_x = nullptr; size_t polish_x_cap = 0;         // host-buffer entry point staging
+  double* polish_E = nullptr;
 };
 
 struct RngTable { int N; int iters; int32_t* sets; };
@@ -107,4 +113,5 @@ struct tv5_ctx {
   cudaStream_t copy_stream = nullptr;   // host-buffer entry point: H2D copies overlap compute
   cudaEvent_t chunk_ev[tv5::kHostChunks] = {};
   cudaEvent_t start_ev = nullptr;
+  int polish_max_ctas = 0;              // co-resident CTAs of irls_polish on this device
 };

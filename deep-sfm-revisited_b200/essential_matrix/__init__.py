@@ -8,14 +8,14 @@ without touching the reference's Python.
   computeP(x1, x2, num_test_points, num_ransac_test_points, num_ransac_iterations, thr)
       -> (E f64 CUDA [3,3], P f64 CUDA [3,4], n_inliers int-like)
   initialise(same six arguments) -> E f64 CUDA [3,3]
-  optimise / decompose / decomposeUV: host-side functions of the reference (polish_E.cu); not on
-      the accelerated path and not provided yet — they raise
-      NotImplementedError rather than silently computing something else.
+  optimise(x1, x2, E_init, delta, alpha, MaxReps) -> E f64 [3,3]   (GPU refinement, tv5_optimise)
+  decompose(E) -> f64 [5] Givens angles;  decomposeUV(E) -> (U, V) f64 [3,3]
 
 `n_inliers` is a LazyCount: it behaves like the Python int the reference returns, but reads the
 device counter (one stream sync) only when its value is actually used.  SFMnet ignores it
 (models/SFMnet.py:267), so the pose stage stays asynchronous.
 """
+import torch as _torch
 import tv5 as _tv5
 
 
@@ -111,16 +111,56 @@ def initialise(input1, input2, num_test_points, num_ransac_test_points, num_rans
     return r.E
 
 
+def _require_double_contiguous(x, name):
+    # CHECK_INPUT_OPT, essential_matrix_wrapper.cpp:43
+    if x.dtype != _torch.float64:
+        raise RuntimeError(f"{name} must be a double tensor")
+    if not x.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
 def optimise(input1, input2, E_init, delta, alpha, MaxReps):
-    raise NotImplementedError("essential_matrix.optimise (host IRLS refinement, polish_E.cu:1470-1577) "
-                              "is outside the accelerated path; see DESIGN.md 'out of scope'")
+    """essential_matrix.optimise — EssentialMatrixOptimiseWrapper, wrapper.cpp:73-87 ->
+    polish_E_robust_parametric (polish_E.cu:1470-1577), which the reference runs on one CPU core
+    over CPU tensors.  Here the refinement runs on the GPU (tv5_optimise): CPU tensors (the
+    reference's calling convention, epipolar_utils.py:76) are copied to the current CUDA device
+    and the result comes back on E_init's device; CUDA tensors are used in place.
+    As in the reference the number of points is input1.size(0) (essential_matrix.cu:86)."""
+    _require_double_contiguous(input1, "input1")
+    _require_double_contiguous(input2, "input2")
+    _require_double_contiguous(E_init, "E_init")
+    n = int(input1.shape[0])
+    if input1.is_cuda:
+        eng = _tv5.get_engine(input1.device)
+        x1 = input1.reshape(-1, 2)[:n]
+        x2 = input2.to(input1.device).reshape(-1, 2)[:n]
+        E = eng.optimise(x1, x2, E_init, float(delta), float(alpha), int(MaxReps))
+        return E.to(E_init.device)
+    eng = _tv5.get_engine()
+    E = eng.optimise_host(input1.reshape(-1, 2)[:n].numpy(), input2.reshape(-1, 2)[:n].numpy(),
+                          E_init.cpu().numpy(), float(delta), float(alpha), int(MaxReps))
+    return _torch.from_numpy(E).to(E_init.device)
 
 
 def decompose(Emat):
-    raise NotImplementedError("essential_matrix.decompose (polish_E.cu:147-338) is outside the "
-                              "accelerated path; see DESIGN.md 'out of scope'")
+    """essential_matrix.decompose — EssentialMatrixDecompose (essential_matrix.cu:29-44 ->
+    Edecomp, polish_E.cu:246-338): the five Givens angles (x, y, z, u, v), float64 [5] on Emat's
+    device.  A CPU tensor is decomposed on the calling thread by libtv5 (as the reference does); a
+    CUDA tensor — a host segfault in the reference — by the device kernel."""
+    if Emat.dtype != _torch.float64:
+        raise RuntimeError("expected scalar type Double but found " + str(Emat.dtype))
+    if Emat.is_cuda:
+        return _tv5.get_engine(Emat.device).decompose_batch(Emat.reshape(1, 3, 3), want_uv=False)["angles"][0]
+    return _torch.from_numpy(_tv5.decompose_host(Emat.contiguous().numpy()))
 
 
 def decomposeUV(Emat):
-    raise NotImplementedError("essential_matrix.decomposeUV (polish_E.cu:147-244) is outside the "
-                              "accelerated path; see DESIGN.md 'out of scope'")
+    """essential_matrix.decomposeUV — EssentialMatrixDecomposeUV (essential_matrix.cu:49-70):
+    (U, V) float64 [3,3] with E ~ U diag(1,1,0) V^T."""
+    if Emat.dtype != _torch.float64:
+        raise RuntimeError("expected scalar type Double but found " + str(Emat.dtype))
+    if Emat.is_cuda:
+        r = _tv5.get_engine(Emat.device).decompose_batch(Emat.reshape(1, 3, 3), want_angles=False)
+        return r["U"][0], r["V"][0]
+    U, V = _tv5.decompose_uv_host(Emat.contiguous().numpy())
+    return _torch.from_numpy(U), _torch.from_numpy(V)

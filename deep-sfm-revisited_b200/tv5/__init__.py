@@ -7,5 +7,5 @@ libtv5.so or a CUDA device is missing.
 """
 from .lib import (Tv5Error, lib_path, load_library, build_library, exported_symbols)  # noqa: F401
 from .engine import (Engine, get_engine, PoseResult, compute_pose, compute_pose_batch,  # noqa: F401
-                     solve5, score, score_bounds, ref_rng_sets)
+                     solve5, score, score_bounds, ref_rng_sets, decompose_host, decompose_uv_host)
 from . import synth  # noqa: F401

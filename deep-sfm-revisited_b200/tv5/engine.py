@@ -242,6 +242,79 @@ class Engine:
         _check(self.ctx, rc, "tv5_ref_rng_sets")
         return out
 
+    # -- decomposition and refinement (polish_E.cu in the reference) ---------------------------
+    def decompose_batch(self, E, want_angles=True, want_uv=True):
+        """E: [B,3,3] (or [3,3]) float64 CUDA -> dict(angles [B,5], U [B,3,3], V [B,3,3])."""
+        if not E.is_cuda or E.dtype != torch.float64:
+            raise RuntimeError("Emat must be a CUDA double tensor")
+        Ef = E.contiguous().view(-1, 9)
+        B = Ef.shape[0]
+        with torch.cuda.device(self.device):
+            ang = torch.empty(B, 5, dtype=torch.float64, device=self.device) if want_angles else None
+            U = torch.empty(B, 3, 3, dtype=torch.float64, device=self.device) if want_uv else None
+            V = torch.empty(B, 3, 3, dtype=torch.float64, device=self.device) if want_uv else None
+            rc = self.L.tv5_decompose_batch(self.ctx, self._stream(), Ef.data_ptr(), B,
+                                            ang.data_ptr() if want_angles else None,
+                                            U.data_ptr() if want_uv else None,
+                                            V.data_ptr() if want_uv else None)
+        _check(self.ctx, rc, "tv5_decompose_batch")
+        return dict(angles=ang, U=U, V=V)
+
+    def optimise(self, x1, x2, E, delta, alpha, max_reps, mask=None, want_iters=False):
+        """Refine E [3,3] on device points x1, x2 [N,2] (optionally only where mask != 0)."""
+        _require_points(x1, "input1")
+        _require_points(x2, "input2")
+        N = x1.shape[0]
+        if x2.shape[0] != N:
+            raise RuntimeError("input1 and input2 must have the same number of points")
+        with torch.cuda.device(self.device):
+            Eo = E.to(device=self.device, dtype=torch.float64).contiguous().clone().view(3, 3)
+            it = torch.zeros(1, dtype=torch.int32, device=self.device) if want_iters else None
+            if mask is not None:
+                mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+                if mask.numel() != N:
+                    raise RuntimeError("mask must have one entry per point")
+            rc = self.L.tv5_optimise(self.ctx, self._stream(), x1.data_ptr(), x2.data_ptr(), N,
+                                     mask.data_ptr() if mask is not None else None, Eo.data_ptr(),
+                                     float(delta), float(alpha), int(max_reps),
+                                     it.data_ptr() if want_iters else None)
+        _check(self.ctx, rc, "tv5_optimise")
+        return (Eo, it) if want_iters else Eo
+
+    def optimise_batch(self, x1, x2, offsets, E, delta, alpha, max_reps, mask=None):
+        """B problems: points concatenated, offsets [B+1] host prefix sums, E [B,3,3]."""
+        _require_points(x1, "input1")
+        _require_points(x2, "input2")
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        B = off.size - 1
+        if B < 1 or off[0] != 0 or off[-1] != x1.shape[0] or x2.shape[0] != x1.shape[0]:
+            raise RuntimeError("offsets must be prefix sums covering all points")
+        with torch.cuda.device(self.device):
+            Eo = E.to(device=self.device, dtype=torch.float64).contiguous().clone().view(B, 3, 3)
+            it = torch.zeros(B, dtype=torch.int32, device=self.device)
+            if mask is not None:
+                mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            rc = self.L.tv5_optimise_batch(self.ctx, self._stream(), B, x1.data_ptr(), x2.data_ptr(),
+                                           off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           mask.data_ptr() if mask is not None else None,
+                                           Eo.data_ptr(), float(delta), float(alpha), int(max_reps),
+                                           it.data_ptr())
+        _check(self.ctx, rc, "tv5_optimise_batch")
+        return Eo, it
+
+    def optimise_host(self, x1, x2, E, delta, alpha, max_reps):
+        """Host numpy in/out (the reference's calling convention: CPU tensors)."""
+        x1 = np.ascontiguousarray(x1, dtype=np.float64)
+        x2 = np.ascontiguousarray(x2, dtype=np.float64)
+        E = np.ascontiguousarray(E, dtype=np.float64).reshape(9)
+        out = np.empty(9)
+        with torch.cuda.device(self.device):
+            rc = self.L.tv5_optimise_host(self.ctx, self._stream(), x1.ctypes.data, x2.ctypes.data,
+                                          int(x1.shape[0]), E.ctypes.data, float(delta), float(alpha),
+                                          int(max_reps), out.ctypes.data)
+        _check(self.ctx, rc, "tv5_optimise_host")
+        return out.reshape(3, 3)
+
     # -- measurement --------------------------------------------------------------------------
     def measure_fp32_peak(self, mode=1):
         v = C.c_double()
@@ -293,6 +366,22 @@ def score(x1, x2, E_list, thr, **kw):
 
 def score_bounds(x1, x2, E_list, thr, **kw):
     return get_engine(x1.device).score_bounds(x1, x2, E_list, thr, **kw)
+
+
+def decompose_host(E):
+    """Five Givens angles of E (host 3x3) — tv5_decompose; needs libtv5.so but no GPU."""
+    E = np.ascontiguousarray(E, dtype=np.float64).reshape(9)
+    out = np.empty(5)
+    _check(None, _lib.load_library().tv5_decompose(E.ctypes.data, out.ctypes.data), "tv5_decompose")
+    return out
+
+
+def decompose_uv_host(E):
+    E = np.ascontiguousarray(E, dtype=np.float64).reshape(9)
+    U, V = np.empty(9), np.empty(9)
+    _check(None, _lib.load_library().tv5_decompose_uv(E.ctypes.data, U.ctypes.data, V.ctypes.data),
+           "tv5_decompose_uv")
+    return U.reshape(3, 3), V.reshape(3, 3)
 
 
 def ref_rng_sets(N, iters, device=None):

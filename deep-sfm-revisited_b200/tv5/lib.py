@@ -96,6 +96,19 @@ def load_library():
     L.tv5_score_bounds.argtypes = [vp, vp, dp, dp, C.c_int, dp, C.c_int, C.c_double, ip, ip]
     L.tv5_ref_rng_sets.restype = C.c_int
     L.tv5_ref_rng_sets.argtypes = [vp, vp, C.c_int, C.c_int, ip]
+    L.tv5_decompose.restype = C.c_int
+    L.tv5_decompose.argtypes = [dp, dp]
+    L.tv5_decompose_uv.restype = C.c_int
+    L.tv5_decompose_uv.argtypes = [dp, dp, dp]
+    L.tv5_decompose_batch.restype = C.c_int
+    L.tv5_decompose_batch.argtypes = [vp, vp, dp, C.c_int, dp, dp, dp]
+    L.tv5_optimise.restype = C.c_int
+    L.tv5_optimise.argtypes = [vp, vp, dp, dp, C.c_int, vp, dp, C.c_double, C.c_double, C.c_int, ip]
+    L.tv5_optimise_batch.restype = C.c_int
+    L.tv5_optimise_batch.argtypes = [vp, vp, C.c_int, dp, dp, C.POINTER(C.c_int64), vp, dp,
+                                     C.c_double, C.c_double, C.c_int, ip]
+    L.tv5_optimise_host.restype = C.c_int
+    L.tv5_optimise_host.argtypes = [vp, vp, dp, dp, C.c_int, dp, C.c_double, C.c_double, C.c_int, dp]
     L.tv5_measure_fp32_peak.restype = C.c_int
     L.tv5_measure_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.tv5_set_force_exact.restype = C.c_int

@@ -163,6 +163,49 @@ int tv5_score_bounds(tv5_ctx* ctx, void* stream, const double* x1, const double*
  */
 int tv5_ref_rng_sets(tv5_ctx* ctx, void* stream, int N, int iters, int32_t* sets_out);
 
+/*
+ * tv5_decompose / tv5_decompose_uv — E = U diag(1,1,0) V^T by three left and two right Givens
+ * rotations; replace EssentialMatrixDecompose / EssentialMatrixDecomposeUV
+ * (essential_matrix.cu:29-70 -> Edecomp, polish_E.cu:147-338; Python `decompose`,
+ * `decomposeUV`).  Like the reference these two take HOST pointers and run on the calling
+ * thread (a 3x3 matrix); results are bit-identical to the reference's.
+ *   E host [9] row-major;  angles host [5] = (x, y, z, u, v);  U, V host [9] row-major.
+ * tv5_decompose_batch is the device form: E device [B,9]; angles [B,5], U [B,9], V [B,9] device,
+ * any of the three may be NULL.
+ */
+int tv5_decompose(const double* E, double* angles);
+int tv5_decompose_uv(const double* E, double* U, double* V);
+int tv5_decompose_batch(tv5_ctx* ctx, void* stream, const double* E, int B, double* angles,
+                        double* U, double* V);
+
+/*
+ * tv5_optimise — iteratively re-weighted Gauss-Newton refinement of E on its five rotation
+ * angles; replaces EssentialMatrixOptimise (essential_matrix.cu:76-105 ->
+ * polish_E_robust_parametric, polish_E.cu:1470-1577; Python `optimise`), which the reference
+ * runs on one CPU core.  Residual e = (V^T x1)_0 (U^T x2)_0 + (V^T x1)_1 (U^T x2)_1, weight 1 if
+ * |e| < delta else alpha*delta/|e|; stops when |J^T W e|^2 < 1e-20 or after max_reps updates.
+ *   x1, x2     device [N,2] float64
+ *   mask       device [N] uint8 or NULL; points with mask == 0 are ignored (extension: lets the
+ *              winner's inlier mask of tv5_compute_pose drive a local-optimisation step)
+ *   E_io       device [9]: initial estimate in, refined E out (||E||_F = sqrt 2 once updated)
+ *   iters_out  device int32 (number of updates applied) or NULL
+ * One cooperative kernel per call; the per-iteration sums are reduced in a fixed order, so a call
+ * is reproducible, but the order differs from the reference's sequential loop: results agree to
+ * rounding (tests: 1e-9), not bit for bit.
+ * tv5_optimise_batch: B independent problems, points concatenated, pt_offsets HOST [B+1],
+ * mask device [sum N] or NULL, E_io device [B,9], iters_out device [B] or NULL.
+ * tv5_optimise_host: all pointers HOST (what the reference's Python passes); copies, runs,
+ * copies E back and synchronises.
+ */
+int tv5_optimise(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
+                 const uint8_t* mask, double* E_io, double delta, double alpha, int max_reps,
+                 int32_t* iters_out);
+int tv5_optimise_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, const double* x2,
+                       const int64_t* pt_offsets, const uint8_t* mask, double* E_io, double delta,
+                       double alpha, int max_reps, int32_t* iters_out);
+int tv5_optimise_host(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
+                      const double* E_init, double delta, double alpha, int max_reps, double* E_out);
+
 /* Testing/diagnostic switch: on != 0 makes the pose entry points score every hypothesis with the
  * float64 scorer (no float32 guard-band pass).  Results are identical by construction; the
  * tests use this to prove it. */

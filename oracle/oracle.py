@@ -52,6 +52,12 @@ def lib():
                                   C.c_double, C.c_int, _dp, _dp, _ip, _ip, _bp]
         L.tv5o_solve_sets.restype = None
         L.tv5o_solve_sets.argtypes = [_dp, _dp, _ip, C.c_int, C.c_int, _dp, _dp, _ip, _ip]
+        L.tv5o_decompose_uv.restype = None
+        L.tv5o_decompose_uv.argtypes = [_dp, _dp, _dp]
+        L.tv5o_decompose_angles.restype = None
+        L.tv5o_decompose_angles.argtypes = [_dp, _dp]
+        L.tv5o_optimise.restype = None
+        L.tv5o_optimise.argtypes = [_dp, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_int]
         _lib = L
     return _lib
 
@@ -161,6 +167,27 @@ def ransac(x1, x2, sets, iters, thr, n_pre=None, n_full=None, with_cheirality=Tr
     if want_mask:
         out["mask"] = mask
     return out
+
+
+def decompose_uv(E):
+    Ew = _f64(E).reshape(9).copy()
+    U = np.zeros(9); V = np.zeros(9)
+    lib().tv5o_decompose_uv(_p(Ew, _dp), _p(U, _dp), _p(V, _dp))
+    return U.reshape(3, 3), V.reshape(3, 3)
+
+
+def decompose_angles(E):
+    Ew = _f64(E).reshape(9).copy()
+    par = np.zeros(5)
+    lib().tv5o_decompose_angles(_p(Ew, _dp), _p(par, _dp))
+    return par
+
+
+def optimise(x1, x2, E, delta, alpha, max_reps):
+    x1, x2 = _f64(x1), _f64(x2)
+    Ew = _f64(E).reshape(9).copy()
+    lib().tv5o_optimise(_p(Ew, _dp), _p(x1, _dp), _p(x2, _dp), x1.shape[0], float(delta), float(alpha), int(max_reps))
+    return Ew.reshape(3, 3)
 
 
 # ---------------------------------------------------------------------------------------------

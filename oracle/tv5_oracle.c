@@ -25,7 +25,7 @@
  * Operation order = the SASS nvcc 12.9 emits for sm_100a with default flags (--fmad=true):
  * the `* 1.0` homogeneous terms fold away, `a*b + c*d` contracts to fma(c,d, a*b), sqrt and
  * division are IEEE round-to-nearest.  Verified bit-for-bit on the GPU box against the
- * reference's own function by tests/test_gpu_reference.py::test_sampson_bits_vs_reference.
+ * reference's own function by tests/test_gpu_parity.py::test_oracle_sampson_bits_match_reference_gpu.
  * ---------------------------------------------------------------------------------------- */
 double tv5o_sampson_err(const double E[9], double x1, double y1, double x2, double y2) {
   double Ex0 = fma(E[1], y1, E[0] * x1) + E[2];
@@ -652,4 +652,109 @@ int tv5o_ransac(const double* x1, const double* x2, int N, const int32_t* sets, 
     else memset(mask, 0, (size_t)n_full);
   }
   return global_best;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Decomposition E = U diag(1,1,0) V^T and IRLS refinement.  ref: polish_E.cu.
+ * ---------------------------------------------------------------------------------------- */
+static void givens_from(double a, double b, double* c, double* s) { /* ref: polish_E.cu:160-165 */
+  double sc = sqrt(a * a + b * b);
+  *c = a / sc;
+  *s = b / sc;
+}
+
+static void decompose_core(double E[9], double cs[10]) { /* ref: polish_E.cu:147-226 / :246-330 */
+  double cx, cy, cz, cu, cv, sx, sy, sz, su, sv, t;
+  givens_from(E[0], -E[3], &cz, &sz);               /* rows 0,1: eliminate E[1][0] */
+  for (int j = 0; j < 3; ++j) { t = E[j] * cz - E[3 + j] * sz; E[3 + j] = E[j] * sz + E[3 + j] * cz; E[j] = t; }
+  givens_from(E[0], -E[6], &cy, &sy);               /* rows 0,2: eliminate E[2][0] */
+  for (int j = 0; j < 3; ++j) { t = E[j] * cy - E[6 + j] * sy; E[6 + j] = E[j] * sy + E[6 + j] * cy; E[j] = t; }
+  givens_from(E[4], -E[7], &cx, &sx);               /* rows 1,2: eliminate E[2][1] */
+  for (int j = 1; j < 3; ++j) E[3 + j] = E[3 + j] * cx - E[6 + j] * sx;
+  givens_from(E[4], -E[5], &cu, &su);               /* columns 1,2: eliminate E[1][2] */
+  E[2] = su * E[1] + cu * E[2];
+  givens_from(E[0], -E[2], &cv, &sv);               /* columns 0,2: eliminate E[0][2] */
+  cs[0] = cx; cs[1] = sx; cs[2] = cy; cs[3] = sy; cs[4] = cz; cs[5] = sz; cs[6] = cu; cs[7] = su; cs[8] = cv; cs[9] = sv;
+}
+
+void tv5o_decompose_uv(double E[9], double U[9], double V[9]) {
+  double k[10];
+  decompose_core(E, k);
+  const double cx = k[0], sx = k[1], cy = k[2], sy = k[3], cz = k[4], sz = k[5], cu = k[6], su = k[7], cv = k[8], sv = k[9];
+  U[0] = cy * cz;  U[1] = -cz * sx * sy + cx * sz; U[2] = cx * cz * sy + sx * sz;
+  U[3] = -cy * sz; U[4] = cx * cz + sx * sy * sz;  U[5] = cz * sx - cx * sy * sz;
+  U[6] = -sy;      U[7] = -cy * sx;                U[8] = cx * cy;
+  V[0] = cv;       V[1] = 0.0; V[2] = sv;
+  V[3] = -su * sv; V[4] = cu;  V[5] = cv * su;
+  V[6] = -cu * sv; V[7] = -su; V[8] = cu * cv;
+}
+
+void tv5o_decompose_angles(double E[9], double par[5]) {
+  double k[10];
+  decompose_core(E, k);
+  for (int i = 0; i < 5; ++i) par[i] = atan2(k[2 * i + 1], k[2 * i]);
+}
+
+static void rot_cols(double M[9], int c1, int c2, double angle) { /* ref: polish_E.cu:128-145 (Gright) */
+  double c = cos(angle), s = sin(angle);
+  for (int i = 0; i < 3; ++i) {
+    double t = M[3 * i + c1] * c - M[3 * i + c2] * s;
+    M[3 * i + c2] = M[3 * i + c1] * s + M[3 * i + c2] * c;
+    M[3 * i + c1] = t;
+  }
+}
+
+static void solve5(double A[5][5], double b[5]) { /* ref: polish_E.cu:340-448 (solve_5x5) */
+  for (int row = 0; row < 5; ++row) {
+    int mr = row;
+    double mv = fabs(A[row][row]);
+    for (int i = row + 1; i < 5; ++i) if (fabs(A[i][row]) > mv) { mv = fabs(A[i][row]); mr = i; }
+    if (mr != row) {
+      for (int j = row; j < 5; ++j) { double t = A[row][j]; A[row][j] = A[mr][j]; A[mr][j] = t; }
+      double t = b[row]; b[row] = b[mr]; b[mr] = t;
+    }
+    for (int i = row + 1; i < 5; ++i) {
+      double f = A[i][row] / A[row][row];
+      for (int j = row + 1; j < 5; ++j) A[i][j] -= f * A[row][j];
+      b[i] -= f * b[row];
+    }
+  }
+  for (int i = 4; i >= 0; --i) {
+    for (int j = i + 1; j < 5; ++j) b[i] -= A[i][j] * b[j];
+    b[i] /= A[i][i];
+  }
+}
+
+void tv5o_optimise(double E[9], const double* x1, const double* x2, int n, double delta,
+                   double alpha, int max_reps) {
+  double U[9], V[9];
+  tv5o_decompose_uv(E, U, V);
+  for (int rep = 0;; ++rep) {
+    double g[5] = {0, 0, 0, 0, 0}, H[5][5];
+    memset(H, 0, sizeof(H));
+    for (int k = 0; k < n; ++k) {
+      double p[3], q[3], J[5];
+      for (int j = 0; j < 3; ++j) {
+        p[j] = x1[2 * k] * V[j] + x1[2 * k + 1] * V[3 + j] + V[6 + j];
+        q[j] = x2[2 * k] * U[j] + x2[2 * k + 1] * U[3 + j] + U[6 + j];
+      }
+      double e = p[0] * q[0] + p[1] * q[1];
+      double w = (fabs(e) < delta) ? 1.0 : alpha * delta / fabs(e);
+      J[0] = -p[1] * q[2]; J[1] = -p[0] * q[2]; J[2] = p[1] * q[0] - p[0] * q[1];
+      J[3] = -p[2] * q[1]; J[4] = -p[2] * q[0];
+      for (int i = 0; i < 5; ++i) {
+        g[i] += J[i] * -e * w;
+        for (int j = 0; j < 5; ++j) H[i][j] += w * J[i] * J[j];
+      }
+    }
+    double mag = 0.0;
+    for (int i = 0; i < 5; ++i) mag += g[i] * g[i];
+    if (mag < 1e-20) break;
+    for (int i = 0; i < 3; ++i)                       /* ref: :60-66 (Eprod) */
+      for (int j = 0; j < 3; ++j) E[3 * i + j] = U[3 * i] * V[3 * j] + U[3 * i + 1] * V[3 * j + 1];
+    if (rep == max_reps) break;
+    solve5(H, g);
+    rot_cols(U, 0, 1, g[2]); rot_cols(U, 0, 2, g[1]); rot_cols(U, 1, 2, g[0]);   /* ref: :450-472 (update) */
+    rot_cols(V, 1, 2, g[3]); rot_cols(V, 0, 2, g[4]);
+  }
 }

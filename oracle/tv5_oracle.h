@@ -61,6 +61,20 @@ void tv5o_solve_sets(const double* x1, const double* x2, const int32_t* sets, in
                      int with_cheirality, double* E_list /*[H,10,9]*/, double* P_list /*[H,10,12]*/,
                      int32_t* n_roots /*[H]*/, int32_t* n_valid /*[H]*/);
 
+/* E = U diag(1,1,0) V^T by three left and two right Givens rotations (Edecomp, polish_E.cu:147-244);
+ * E is overwritten with the reduced matrix exactly as the reference does.  U, V row-major. */
+void tv5o_decompose_uv(double E[9], double U[9], double V[9]);
+
+/* The five Givens angles (x, y, z, u, v) of the same decomposition (Edecomp, polish_E.cu:246-338). */
+void tv5o_decompose_angles(double E[9], double par[5]);
+
+/* Iteratively re-weighted least-squares refinement of E on n correspondences
+ * (polish_E_robust_parametric, polish_E.cu:1470-1577): residual eps = first two components of
+ * (x1 V).(x2 U), weight 1 if |eps| < delta else alpha*delta/|eps|, Gauss-Newton on the 5 angles,
+ * stops when |J^T W eps|^2 < 1e-20 or after max_reps updates.  E is updated in place. */
+void tv5o_optimise(double E[9], const double* x1, const double* x2, int n, double delta,
+                   double alpha, int max_reps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,5 +65,25 @@ def test_shim_signatures_and_errors():
         x = torch.zeros(10, 2, dtype=torch.float64)
         with pytest.raises((RuntimeError, tv5.Tv5Error)):
             em.computeP(x, x, 10, 10, 1, 1e-4)
-    with pytest.raises(NotImplementedError):
-        em.decompose(torch.eye(3, dtype=torch.float64))
+    with pytest.raises(RuntimeError, match="must be a double tensor"):
+        em.optimise(torch.zeros(4, 2), torch.zeros(4, 2, dtype=torch.float64), torch.eye(3, dtype=torch.float64), 1e-4, 1.0, 3)
+    with pytest.raises(RuntimeError, match="E_init must be contiguous"):
+        em.optimise(torch.zeros(4, 2, dtype=torch.float64), torch.zeros(4, 2, dtype=torch.float64),
+                    torch.ones(3, 3, dtype=torch.float64).t(), 1e-4, 1.0, 3)
+
+
+def test_host_decompose_matches_reference_golden():
+    """tv5_decompose / tv5_decompose_uv run on the host like the reference's Edecomp
+    (polish_E.cu:147-338); bit-identical to the reference extension's outputs."""
+    import numpy as np
+    import essential_matrix as em
+    g = np.load(os.path.join(ROOT, "tests", "golden", "polish_ref.npz"))
+    for i in range(g["E"].shape[0]):
+        E = torch.from_numpy(g["E"][i].copy())
+        U, V = em.decomposeUV(E)
+        a = em.decompose(E)
+        assert (U.numpy() == g["U"][i]).all() and (V.numpy() == g["V"][i]).all()   # bit-exact
+        assert (a.numpy() == g["angles"][i]).all()
+        assert a.dtype == torch.float64 and a.shape == (5,) and U.shape == (3, 3)
+    with pytest.raises(RuntimeError):
+        em.decompose(torch.eye(3))

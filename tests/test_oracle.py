@@ -168,3 +168,44 @@ def test_oracle_against_live_reference_build():
     mine = oracle.solve_sets(sc["x1"], sc["x2"], sets, True)
     assert (mine["n_roots"] == ref["n_roots"]).mean() > 0.995
     assert (mine["n_valid"] == ref["n_valid"]).mean() > 0.995
+
+
+# ---------------------------------------------------------------------------------------------
+# decomposition and refinement (polish_E.cu) against the reference extension's host functions
+# ---------------------------------------------------------------------------------------------
+POLISH_KEYS = ("0.0001_1_0", "0.0001_1_1", "0.0001_1_10", "0.0001_0_10", "0.0005_0.5_200")
+
+
+@pytest.fixture(scope="module")
+def gold_polish(golden_dir):
+    return np.load(os.path.join(golden_dir, "polish_ref.npz"))
+
+
+def test_decompose_bit_exact_vs_reference(gold_polish):
+    g = gold_polish
+    for i in range(g["E"].shape[0]):
+        U, V = oracle.decompose_uv(g["E"][i])
+        assert (U == g["U"][i]).all() and (V == g["V"][i]).all()
+        assert (oracle.decompose_angles(g["E"][i]) == g["angles"][i]).all()
+        E3 = U @ np.diag([1.0, 1.0, 0.0]) @ V.T
+        En = g["E"][i] / np.linalg.norm(g["E"][i]) * np.sqrt(2.0)
+        assert min(np.abs(E3 - En).max(), np.abs(E3 + En).max()) < 5e-3   # inputs are E_gt + 1e-3 noise
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_optimise_bit_exact_vs_reference(gold_polish, case):
+    g = gold_polish
+    for key in POLISH_KEYS:
+        delta, alpha, reps = key.split("_")
+        E = oracle.optimise(g[f"opt{case}_x1"], g[f"opt{case}_x2"], g[f"opt{case}_E0"], float(delta),
+                            float(alpha), int(reps))
+        assert (E == g[f"opt{case}_{key}"]).all()      # same sequential sums: bit-exact
+
+
+def test_optimise_improves_towards_ground_truth(gold_polish):
+    g = gold_polish
+    for case in range(3):
+        Egt = g[f"opt{case}_Egt"]
+        d0 = synth.essential_distance(g[f"opt{case}_E0"], Egt)
+        E = oracle.optimise(g[f"opt{case}_x1"], g[f"opt{case}_x2"], g[f"opt{case}_E0"], 1e-4, 1.0, 10)
+        assert synth.essential_distance(E, Egt) < 0.25 * d0
