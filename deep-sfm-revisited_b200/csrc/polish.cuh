@@ -49,7 +49,11 @@ __host__ __device__ __forceinline__ Rot rot_annihilating(double keep, double kil
 struct Givens5 {
   Rot x, y, z, u, v;
 };
-__host__ __device__ inline Givens5 givens_decompose(const double Ein[9]) {
+// `reduced` (optional) receives the working matrix as the reference leaves it in its in/out
+// argument — only the entries the later steps read are kept up to date.  The reference's
+// `optimise` returns exactly that when it stops before the first update (zero gradient), and
+// so does irls_polish.
+__host__ __device__ inline Givens5 givens_decompose(const double Ein[9], double* reduced = nullptr) {
   double E[9];
   for (int i = 0; i < 9; ++i) E[i] = Ein[i];
   Givens5 g;
@@ -70,6 +74,8 @@ __host__ __device__ inline Givens5 givens_decompose(const double Ein[9]) {
   g.u = rot_annihilating(E[4], E[5]);
   E[2] = add_nc(mul_nc(g.u.s, E[1]), mul_nc(g.u.c, E[2]));
   g.v = rot_annihilating(E[0], E[2]);
+  if (reduced)
+    for (int i = 0; i < 9; ++i) reduced[i] = E[i];
   return g;
 }
 
@@ -195,8 +201,9 @@ __global__ void __launch_bounds__(kPolishThreads) irls_polish(const PolishJob* _
   if (tid == 0) {
     double e[9], u[9], v[9];
     for (int i = 0; i < 9; ++i) e[i] = J.E[i];
-    givens_to_uv(givens_decompose(e), u, v);
-    for (int i = 0; i < 9; ++i) { s_U[i] = u[i]; s_V[i] = v[i]; s_E[i] = e[i]; }
+    double red[9];
+    givens_to_uv(givens_decompose(e, red), u, v);
+    for (int i = 0; i < 9; ++i) { s_U[i] = u[i]; s_V[i] = v[i]; s_E[i] = red[i]; }
     s_stop = 0;
   }
   __syncthreads();

@@ -433,9 +433,11 @@ def test_optimise_edge_cases_and_determinism(engine, gold_polish):
     a, ia = engine.optimise(x1, x2, E0, 1e-4, 1.0, 10, want_iters=True)
     b, ib = engine.optimise(x1, x2, E0, 1e-4, 1.0, 10, want_iters=True)
     assert torch.equal(a, b) and int(ia) == int(ib) == 10           # run-to-run identical
-    # no points: the gradient is zero, E comes back untouched (reference: break before Eprod)
+    # no points: the gradient is zero and, like the reference (break before Eprod,
+    # polish_E.cu:1545), the half-reduced working matrix of the decomposition comes back
     z = torch.zeros(0, 2, dtype=torch.float64, device="cuda")
-    assert torch.equal(engine.optimise(z, z, E0, 1e-4, 1.0, 5), E0)
+    E_none = engine.optimise(z, z, E0, 1e-4, 1.0, 5).cpu().numpy()
+    assert (E_none == oracle.optimise(np.zeros((0, 2)), np.zeros((0, 2)), g["opt2_E0"], 1e-4, 1.0, 5)).all()
     # mask == inlier subset is the same as passing the subset
     m = (torch.arange(x1.shape[0], device="cuda") % 3 != 0)
     sub = engine.optimise(x1[m].contiguous(), x2[m].contiguous(), E0, 1e-4, 1.0, 6)
