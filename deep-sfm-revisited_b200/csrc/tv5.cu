@@ -24,6 +24,7 @@
 #include "solve5.cuh"
 #include "solve5_coop.cuh"
 #include "polish.cuh"
+#include "flow_points.cuh"
 #include "tv5_internal.h"
 
 namespace tv5 {
@@ -870,7 +871,7 @@ int tv5_destroy(tv5_ctx* ctx) {
   void* ptrs[] = {w.desc, w.state, w.ctl, w.pp, w.E_list, w.P_list, w.n_valid, w.n_roots, w.hyp,
                   w.hyp_id, w.notin, w.out, w.cand, w.cand_cnt, w.h2d_x, w.h2d_sets, w.out_E,
                   w.out_P, w.out_res, w.polish_jobs, w.polish_partial, w.polish_barrier,
-                  w.polish_x, w.polish_E};
+                  w.polish_x, w.polish_E, w.flow_jobs, w.flow_x, w.flow_EP};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& t : ctx->rng_tables) cudaFree(t.sets);
@@ -1300,6 +1301,98 @@ int tv5_optimise_host(tv5_ctx* ctx, void* stream, const double* x1, const double
   if (rc) return rc;
   TV5_CUDA(ctx, cudaMemcpyAsync(E_out, w.polish_E, 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TV5_CUDA(ctx, cudaStreamSynchronize(st));
+  return TV5_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// optical flow -> correspondences (flow_points.cuh)
+// ------------------------------------------------------------------------------------------
+static int flow_offsets(int B, int H, int W, int mode, int margin, const int64_t* pt_offsets,
+                        std::vector<int64_t>& off) {
+  off.assign((size_t)B + 1, 0);
+  if (mode == kFlowCrop) {
+    if (margin < 0 || 2 * margin >= H || 2 * margin >= W) return TV5_ERR_INVALID;
+    const int64_t n = (int64_t)(H - 2 * margin) * (W - 2 * margin);
+    for (int b = 0; b <= B; ++b) off[b] = n * b;
+  } else {
+    if (!pt_offsets) return TV5_ERR_INVALID;
+    for (int b = 0; b <= B; ++b) off[b] = pt_offsets[b] - pt_offsets[0];
+    for (int b = 0; b < B; ++b)
+      if (off[b + 1] < off[b]) return TV5_ERR_INVALID;
+  }
+  return off[B] > 0x3fffffff ? TV5_ERR_INVALID : TV5_OK;
+}
+
+int tv5_flow_to_points(tv5_ctx* ctx, void* stream, const float* flow, int B, int H, int W,
+                       const float* Kinv, int mode, int margin, const void* pts,
+                       const int64_t* pt_offsets, double* x1_out, double* x2_out) {
+  if (!ctx || !flow || B < 1 || H < 1 || W < 1 || !Kinv || mode < 0 || mode > 2 || !x1_out || !x2_out)
+    return TV5_ERR_INVALID;
+  if (mode != kFlowCrop && !pts) return TV5_ERR_INVALID;
+  if (B > 65535) return TV5_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<int64_t> off;
+  int rc = flow_offsets(B, H, W, mode, margin, pt_offsets, off);
+  if (rc) return rc;
+  Workspace& w = ctx->ws;
+  FlowJob* jobs = (FlowJob*)w.flow_jobs;
+  if ((size_t)B > w.flow_jobs_cap || !jobs) {
+    if ((rc = grow_same(ctx, jobs, w.flow_jobs_cap, (size_t)B))) { w.flow_jobs = nullptr; w.flow_jobs_cap = 0; return rc; }
+    w.flow_jobs = jobs;
+    w.flow_jobs_cap = (size_t)B;
+  }
+  std::vector<FlowJob> hj((size_t)B);
+  int64_t max_n = 0;
+  const size_t elem = mode == kFlowGather ? sizeof(int32_t) : sizeof(float);
+  for (int b = 0; b < B; ++b) {
+    FlowJob& j = hj[b];
+    j.flow = flow + (size_t)b * 2 * H * W;
+    j.Kinv = Kinv + 9 * (size_t)b;
+    j.pts = mode == kFlowCrop ? nullptr : (const char*)pts + (size_t)off[b] * 2 * elem;
+    j.out_off = off[b];
+    j.n = (int32_t)(off[b + 1] - off[b]);
+    j.crop_w = W - 2 * margin;
+    j.margin = margin;
+    j.pad = 0;
+    max_n = std::max<int64_t>(max_n, j.n);
+  }
+  if (max_n == 0) return TV5_OK;
+  TV5_CUDA(ctx, cudaMemcpyAsync(jobs, hj.data(), sizeof(FlowJob) * B, cudaMemcpyHostToDevice, st));
+  flow_points<<<dim3((unsigned)((max_n + 255) / 256), B), 256, 0, st>>>(jobs, H, W, mode, (double2*)x1_out,
+                                                                       (double2*)x2_out);
+  TV5_CUDA(ctx, cudaGetLastError());
+  return TV5_OK;
+}
+
+int tv5_pose_from_flow(tv5_ctx* ctx, void* stream, const float* flow, int B, int H, int W,
+                       const float* Kinv, int mode, int margin, const void* pts,
+                       const int64_t* pt_offsets, const int32_t* sets, int iters, double thr,
+                       int with_cheirality, float* E32_out, float* P32_out, tv5_result* result,
+                       double* E_out, double* P_out) {
+  if (!ctx || B < 1 || !result || (!E32_out && !E_out)) return TV5_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<int64_t> off;
+  int rc = flow_offsets(B, H, W, mode, margin, pt_offsets, off);
+  if (rc) return rc;
+  for (int b = 0; b < B; ++b)
+    if (off[b + 1] == off[b]) return TV5_ERR_INVALID;   // a pair without correspondences
+  Workspace& w = ctx->ws;
+  if ((rc = grow(ctx, w.flow_x, w.flow_x_cap, (size_t)off[B] * 4))) return rc;
+  if ((rc = grow(ctx, w.flow_EP, w.flow_EP_cap, (size_t)B * 21))) return rc;
+  double* x1 = w.flow_x;
+  double* x2 = w.flow_x + 2 * (size_t)off[B];
+  double* E64 = E_out ? E_out : w.flow_EP;
+  double* P64 = P_out ? P_out : w.flow_EP + 9 * (size_t)B;
+  if ((rc = tv5_flow_to_points(ctx, stream, flow, B, H, W, Kinv, mode, margin, pts, pt_offsets, x1, x2))) return rc;
+  if ((rc = tv5_compute_pose_batch(ctx, stream, B, x1, x2, off.data(), sets, iters, 0, 0, thr, with_cheirality,
+                                   E64, P64, result, nullptr)))
+    return rc;
+  if (E32_out || P32_out) {
+    pose_to_float<<<(B * 12 + 127) / 128, 128, 0, st>>>(E64, P64, B, E32_out, P32_out);
+    TV5_CUDA(ctx, cudaGetLastError());
+  }
   return TV5_OK;
 }
 

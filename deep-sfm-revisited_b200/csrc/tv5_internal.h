@@ -92,6 +92,10 @@ struct Workspace {
   unsigned int* polish_barrier = nullptr;
   double* polish_x = nullptr; size_t polish_x_cap = 0;         // host-buffer entry point staging
   double* polish_E = nullptr;
+  // flow -> correspondences (flow_points.cuh)
+  void* flow_jobs = nullptr; size_t flow_jobs_cap = 0;         // [B] FlowJob
+  double* flow_x = nullptr; size_t flow_x_cap = 0;             // x1 | x2 of tv5_pose_from_flow
+  double* flow_EP = nullptr; size_t flow_EP_cap = 0;           // [B,9] | [B,12] float64 results
 };
 
 struct RngTable { int N; int iters; int32_t* sets; };

@@ -242,6 +242,78 @@ class Engine:
         _check(self.ctx, rc, "tv5_ref_rng_sets")
         return out
 
+    # -- optical flow -> correspondences (front of pose_by_ransac, models/SFMnet.py:176-272) ---
+    def _flow_args(self, flow, Kinv, margin, pts, offsets):
+        if not isinstance(flow, torch.Tensor) or not flow.is_cuda or flow.dtype != torch.float32:
+            raise RuntimeError("flow must be a CUDA float tensor")
+        if flow.dim() != 4 or flow.shape[1] != 2:
+            raise RuntimeError("flow must have shape [B, 2, H, W]")
+        flow = flow.contiguous()
+        B, _, H, W = flow.shape
+        Kinv = Kinv.to(device=self.device, dtype=torch.float32).contiguous()
+        if Kinv.numel() != B * 9:
+            raise RuntimeError("intrinsic_inv must have shape [B, 3, 3]")
+        if pts is None:
+            mode, off, pp = 0, None, None
+            n = (H - 2 * margin) * (W - 2 * margin)
+            if margin < 0 or 2 * margin >= min(H, W):
+                raise RuntimeError("margin leaves no pixels")
+            counts = np.full(B, n, dtype=np.int64)
+        else:
+            if not isinstance(pts, torch.Tensor):
+                raise RuntimeError("pts must be a tensor [sum n, 2] of (x, y)")
+            if pts.dtype in (torch.int32, torch.int64, torch.int16):
+                mode, pts = 1, pts.to(device=self.device, dtype=torch.int32).contiguous()
+            else:
+                mode, pts = 2, pts.to(device=self.device, dtype=torch.float32).contiguous()
+            off = np.ascontiguousarray(offsets if offsets is not None else [0, pts.shape[0]], dtype=np.int64)
+            if off.size != B + 1 or off[0] != 0 or off[-1] != pts.shape[0] or pts.dim() != 2 or pts.shape[1] != 2:
+                raise RuntimeError("offsets must be [B+1] prefix sums covering pts [sum n, 2]")
+            counts = np.diff(off)
+            pp = pts
+        return flow, Kinv, B, H, W, mode, pp, off, counts
+
+    def flow_to_points(self, flow, Kinv, margin=10, pts=None, offsets=None):
+        """flow [B,2,H,W] f32, Kinv [B,3,3] -> (x1, x2 f64 [sum n, 2], offsets [B+1]).
+        pts None: dense crop with `margin`; int tensor [sum n,2] (x,y): pixel gather; float tensor:
+        bilinear sampling (cfg.SAMPLE_SP)."""
+        flow, Kinv, B, H, W, mode, pp, off, counts = self._flow_args(flow, Kinv, margin, pts, offsets)
+        total = int(counts.sum())
+        with torch.cuda.device(self.device):
+            x1 = torch.empty(total, 2, dtype=torch.float64, device=self.device)
+            x2 = torch.empty(total, 2, dtype=torch.float64, device=self.device)
+            rc = self.L.tv5_flow_to_points(
+                self.ctx, self._stream(), flow.data_ptr(), B, H, W, Kinv.data_ptr(), mode, int(margin),
+                pp.data_ptr() if pp is not None else None,
+                off.ctypes.data_as(C.POINTER(C.c_int64)) if off is not None else None,
+                x1.data_ptr(), x2.data_ptr())
+        _check(self.ctx, rc, "tv5_flow_to_points")
+        return x1, x2, np.concatenate([[0], np.cumsum(counts)])
+
+    def pose_from_flow(self, flow, Kinv, iters, thr, margin=10, pts=None, offsets=None, sets=None,
+                       with_cheirality=True):
+        """The geometric part of SFMnet.pose_by_ransac in one submission: returns
+        (P_mat f32 [B,3,4], E_mat f32 [B,3,3], PoseResult with the float64 E/P and the counters)."""
+        flow, Kinv, B, H, W, mode, pp, off, counts = self._flow_args(flow, Kinv, margin, pts, offsets)
+        with torch.cuda.device(self.device):
+            E32 = torch.empty(B, 3, 3, dtype=torch.float32, device=self.device)
+            P32 = torch.empty(B, 3, 4, dtype=torch.float32, device=self.device)
+            E = torch.empty(B, 3, 3, dtype=torch.float64, device=self.device)
+            P = torch.empty(B, 3, 4, dtype=torch.float64, device=self.device)
+            stats = torch.empty(B, 8, dtype=torch.int32, device=self.device)
+            sp = None
+            if sets is not None:
+                sets = self._sets(sets, iters, B)
+                sp = sets.data_ptr()
+            rc = self.L.tv5_pose_from_flow(
+                self.ctx, self._stream(), flow.data_ptr(), B, H, W, Kinv.data_ptr(), mode, int(margin),
+                pp.data_ptr() if pp is not None else None,
+                off.ctypes.data_as(C.POINTER(C.c_int64)) if off is not None else None,
+                sp, int(iters), float(thr), int(bool(with_cheirality)), E32.data_ptr(), P32.data_ptr(),
+                stats.data_ptr(), E.data_ptr(), P.data_ptr())
+        _check(self.ctx, rc, "tv5_pose_from_flow")
+        return P32, E32, PoseResult(E, P, stats)
+
     # -- decomposition and refinement (polish_E.cu in the reference) ---------------------------
     def decompose_batch(self, E, want_angles=True, want_uv=True):
         """E: [B,3,3] (or [3,3]) float64 CUDA -> dict(angles [B,5], U [B,3,3], V [B,3,3])."""

@@ -109,6 +109,13 @@ def load_library():
                                      C.c_double, C.c_double, C.c_int, ip]
     L.tv5_optimise_host.restype = C.c_int
     L.tv5_optimise_host.argtypes = [vp, vp, dp, dp, C.c_int, dp, C.c_double, C.c_double, C.c_int, dp]
+    L.tv5_flow_to_points.restype = C.c_int
+    L.tv5_flow_to_points.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp,
+                                     C.POINTER(C.c_int64), dp, dp]
+    L.tv5_pose_from_flow.restype = C.c_int
+    L.tv5_pose_from_flow.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp,
+                                     C.POINTER(C.c_int64), ip, C.c_int, C.c_double, C.c_int, vp, vp,
+                                     vp, dp, dp]
     L.tv5_measure_fp32_peak.restype = C.c_int
     L.tv5_measure_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.tv5_set_force_exact.restype = C.c_int

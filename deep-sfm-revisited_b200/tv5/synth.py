@@ -98,3 +98,26 @@ def essential_distance(Ea, Eb):
     a = Ea / np.linalg.norm(Ea)
     b = Eb / np.linalg.norm(Eb)
     return float(min(np.linalg.norm(a - b), np.linalg.norm(a + b)))
+
+
+def make_flow(hw=KITTI_HW, seed=1234, rvec=(0.002, 0.01, -0.001), t=(0.03, -0.01, -0.8), noise_px=0.05,
+              outlier_frac=0.2, outlier_px=30.0, K=KITTI_K):
+    """Dense synthetic optical flow [2,H,W] float32 of a rigid scene with random depth (what the
+    flow network of SFMnet would output, models/SFMnet.py:120-122), plus ground truth."""
+    rng = np.random.default_rng(seed)
+    H, W = hw
+    v, u = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+    depth = rng.uniform(5.0, 80.0, (H, W))
+    R = rodrigues(rvec)
+    t = np.asarray(t, dtype=np.float64)
+    Kinv = np.linalg.inv(K)
+    p1 = np.stack([u, v, np.ones((H, W))], 0).reshape(3, -1)
+    X2 = R @ ((Kinv @ p1) * depth.reshape(1, -1)) + t[:, None]
+    p2 = (K @ (X2 / X2[2:3])).reshape(3, H, W)
+    du = p2[0] - u + rng.normal(0.0, noise_px, (H, W))
+    dv = p2[1] - v + rng.normal(0.0, noise_px, (H, W))
+    is_out = rng.uniform(0, 1, (H, W)) < outlier_frac
+    du = du + is_out * rng.uniform(-outlier_px, outlier_px, (H, W))
+    dv = dv + is_out * rng.uniform(-outlier_px, outlier_px, (H, W))
+    return dict(flow=np.stack([du, dv]).astype(np.float32), Kinv=Kinv.astype(np.float32), R=R,
+                t=t / np.linalg.norm(t), E_gt=essential_from_pose(R, t))

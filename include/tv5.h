@@ -206,6 +206,36 @@ int tv5_optimise_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, cons
 int tv5_optimise_host(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
                       const double* E_init, double delta, double alpha, int max_reps, double* E_out);
 
+/*
+ * tv5_flow_to_points — optical flow -> K^-1-normalised correspondences in one pass; replaces the
+ * per-image tensor chain in front of every pose solve in the reference: flow2coord
+ * (models/SFMnet.py:298-318), the point selection of pose_by_ransac (:239-254), bmm(K^-1, .)
+ * (:259-260), transpose/[:, :2]/contiguous (:262-263) and .double() (epipolar_utils.py:130).
+ *   flow        device [B,2,H,W] float32 (channel 0 = dx, 1 = dy)
+ *   Kinv        device [B,3,3] float32 inverse intrinsics
+ *   mode        0 dense crop [margin,H-margin) x [margin,W-margin) row-major (SFMnet.py:240-241)
+ *               1 integer pixel list: pts device int32 [sum n,2] = (x, y) (SFMnet.py:251-254)
+ *               2 sub-pixel list: pts device float32 [sum n,2], bilinear, align_corners=True,
+ *                 zero padding (cfg.SAMPLE_SP, SFMnet.py:244-249)
+ *   pt_offsets  HOST [B+1] prefix sums of the list lengths (modes 1, 2; ignored for mode 0)
+ *   x1_out, x2_out  device [sum n,2] float64 — exactly the arrays the reference passes to
+ *               `essential_matrix.computeP`: all arithmetic in float32 as in the reference,
+ *               widened at the end.
+ * tv5_pose_from_flow — the same followed by tv5_compute_pose_batch on all points of each image
+ * (n_pre = n_full = n, what SFMnet passes) in one stream-ordered submission without
+ * intermediate tensors; E32_out [B,9] / P32_out [B,12] are the float32 E_mat / P_mat tensors
+ * pose_by_ransac returns (SFMnet.py:186-187,272); E_out / P_out (float64, optional) the
+ * unrounded ones.
+ */
+int tv5_flow_to_points(tv5_ctx* ctx, void* stream, const float* flow, int B, int H, int W,
+                       const float* Kinv, int mode, int margin, const void* pts,
+                       const int64_t* pt_offsets, double* x1_out, double* x2_out);
+int tv5_pose_from_flow(tv5_ctx* ctx, void* stream, const float* flow, int B, int H, int W,
+                       const float* Kinv, int mode, int margin, const void* pts,
+                       const int64_t* pt_offsets, const int32_t* sets, int iters, double thr,
+                       int with_cheirality, float* E32_out, float* P32_out, tv5_result* result,
+                       double* E_out, double* P_out);
+
 /* Testing/diagnostic switch: on != 0 makes the pose entry points score every hypothesis with the
  * float64 scorer (no float32 guard-band pass).  Results are identical by construction; the
  * tests use this to prove it. */

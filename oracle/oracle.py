@@ -225,3 +225,68 @@ def ref_solve_sets(x1, x2, sets):
                                    _p(P_valid, _dp), _p(nv, _ip))
     assert rc == 0
     return dict(E_all=E_all, n_roots=nr, E=E_valid, P=P_valid, n_valid=nv)
+
+
+# ---------------------------------------------------------------------------------------------
+# optical flow -> normalised correspondences (front of pose_by_ransac), numpy float32
+# ---------------------------------------------------------------------------------------------
+def flow_to_points(flow, Kinv, margin=10, pts=None):
+    """One image.  flow [2,H,W] float32, Kinv [3,3] float32 -> x1, x2 [n,2] float64.
+
+    Restates, in float32 like the reference, flow2coord (models/SFMnet.py:298-318: pixel grid,
+    grid + flow, homogeneous one), the selection of pose_by_ransac (dense crop :240-241 when
+    pts is None; integer gather :251-254 for an integer (x, y) list; bilinear grid_sample with
+    align_corners=True and zero padding :244-249 for a float list), bmm(K^-1, .) (:259-260),
+    the [:, :2] slice (:262-263) and .double() (epipolar_utils.py:130).  The three-term
+    products with K^-1 are accumulated k = 0, 1, 2 with fused multiply-adds like an SGEMM inner
+    loop (emulated exactly in float64: a float32 product is exact there)."""
+    f32 = np.float32
+    flow = np.asarray(flow, dtype=f32)
+    K = np.asarray(Kinv, dtype=f32)
+    _, H, W = flow.shape
+    gx = np.broadcast_to(np.arange(W, dtype=f32)[None, :], (H, W))
+    gy = np.broadcast_to(np.arange(H, dtype=f32)[:, None], (H, W))
+    c1 = np.stack([gx, gy, np.ones((H, W), f32)])                  # [3,H,W]
+    c2 = np.stack([gx + flow[0], gy + flow[1], np.ones((H, W), f32)])
+    if pts is None:
+        a = c1[:, margin:H - margin, margin:W - margin].reshape(3, -1)
+        b = c2[:, margin:H - margin, margin:W - margin].reshape(3, -1)
+    elif np.issubdtype(np.asarray(pts).dtype, np.integer):
+        p = np.asarray(pts)
+        a, b = c1[:, p[:, 1], p[:, 0]], c2[:, p[:, 1], p[:, 0]]
+    else:
+        p = np.asarray(pts, dtype=f32)
+        gxn = f32(2.0) * p[:, 0] / f32(max(W - 1, 1)) - f32(1.0)
+        gyn = f32(2.0) * p[:, 1] / f32(max(H - 1, 1)) - f32(1.0)
+        ix = ((gxn + f32(1.0)) / f32(2.0)) * f32(W - 1)
+        iy = ((gyn + f32(1.0)) / f32(2.0)) * f32(H - 1)
+        x0, y0 = np.floor(ix), np.floor(iy)
+        wx1, wx0, wy1, wy0 = ix - x0, (x0 + f32(1.0)) - ix, iy - y0, (y0 + f32(1.0)) - iy
+        a = np.zeros((3, p.shape[0]), f32)
+        b = np.zeros((3, p.shape[0]), f32)
+        for dx, dy, w in ((0, 0, wx0 * wy0), (1, 0, wx1 * wy0), (0, 1, wx0 * wy1), (1, 1, wx1 * wy1)):
+            xs, ys = x0.astype(np.int64) + dx, y0.astype(np.int64) + dy
+            ok = (xs >= 0) & (xs < W) & (ys >= 0) & (ys < H)
+            xc, yc = np.clip(xs, 0, W - 1), np.clip(ys, 0, H - 1)
+            for ch in range(3):
+                for dst, src in ((a, c1), (b, c2)):
+                    term = _fma32(src[ch, yc, xc], w, dst[ch])
+                    dst[ch] = np.where(ok, term, dst[ch])
+
+    def apply(c):
+        out = np.empty((c.shape[1], 2), np.float64)
+        for r in range(2):
+            acc = (K[r, 0] * c[0]).astype(f32)
+            acc = _fma32(K[r, 1], c[1], acc)
+            acc = _fma32(K[r, 2], c[2], acc)
+            out[:, r] = acc.astype(np.float64)
+        return out
+
+    return apply(a), apply(b)
+
+
+def _fma32(a, b, c):
+    """float32 fused multiply-add: the product of two float32 is exact in float64 and the sum of
+    it with a float32 needs < 2*53 bits only in far-apart-exponent cases that the final rounding
+    to float32 absorbs (double rounding can differ in 1 ulp; the tests allow it)."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)

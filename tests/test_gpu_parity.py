@@ -465,3 +465,78 @@ def test_local_optimisation_after_ransac_improves_pose(engine, std_pair):
     assert d1 <= d0 * 1.05 and d1 < 2e-3
     cnt = engine.score(x1, x2, dev(E.reshape(1, 9)), THR).cpu().numpy()[0]
     assert cnt >= r.count - 20
+
+
+# ---------------------------------------------------------------------------------------------
+# flow -> correspondences -> pose (front of SFMnet.pose_by_ransac)
+# ---------------------------------------------------------------------------------------------
+def _flow_batch(hw, B, seed=0):
+    scs = [synth.make_flow(hw=hw, seed=seed + i, rvec=(0.002, 0.01 + 0.002 * i, -0.001)) for i in range(B)]
+    flow = np.stack([s["flow"] for s in scs])
+    Kinv = np.stack([s["Kinv"] for s in scs])
+    return scs, flow, Kinv
+
+
+@pytest.mark.parametrize("hw", [(48, 80), (370, 1226)])
+def test_flow_to_points_matches_oracle_and_reference_torch_chain(engine, hw):
+    import ref_flow_torch as rf
+    H, W = hw
+    B = 2
+    scs, flow, Kinv = _flow_batch(hw, B)
+    tf, tk = dev(flow, torch.float32), dev(Kinv, torch.float32)
+    rng = np.random.default_rng(9)
+    n = [37, 64]
+    pts_i = np.stack([rng.integers(0, W, sum(n)), rng.integers(0, H, sum(n))], 1).astype(np.int32)
+    pts_f = np.stack([rng.uniform(0, W - 1, sum(n)), rng.uniform(0, H - 1, sum(n))], 1).astype(np.float32)
+    pts_f[0] = (W - 1, H - 1)
+    off = np.array([0, n[0], sum(n)])
+    ulp = float(np.finfo(np.float32).eps)
+    for name, pts in (("crop", None), ("gather", pts_i), ("bilinear", pts_f)):
+        x1, x2, o = engine.flow_to_points(tf, tk, 10, None if pts is None else torch.from_numpy(pts),
+                                          None if pts is None else off)
+        x1, x2 = x1.cpu().numpy(), x2.cpu().numpy()
+        for b in range(B):
+            p = None if pts is None else pts[off[b]:off[b + 1]]
+            oa, oc = oracle.flow_to_points(flow[b], Kinv[b], 10, p)
+            ma, mc = x1[o[b]:o[b + 1]], x2[o[b]:o[b + 1]]
+            assert ma.shape == oa.shape
+            # same float32 operation sequence as the oracle: bit-exact, except the bilinear mode
+            # where the oracle's emulated fma can double-round (1 ulp)
+            tol = 0.0 if name != "bilinear" else ulp * max(1.0, np.abs(oc).max())
+            assert np.abs(ma - oa).max() <= tol and np.abs(mc - oc).max() <= tol, name
+            # the reference's own torch ops on this GPU (cuBLAS bmm, cuDNN-free grid_sample): 1 ulp
+            kw = {} if pts is None else (dict(pts=p.astype(np.float64)) if name == "gather"
+                                         else dict(pts=p.astype(np.float64), sample_sp=True))
+            ta, tc = rf.points_of_image(tf, tk, b, 10, **kw)
+            tol = ulp * max(1.0, np.abs(oc).max())
+            assert np.abs(ma - ta.cpu().numpy()).max() <= tol, name
+            assert np.abs(mc - tc.cpu().numpy()).max() <= tol, name
+
+
+def test_pose_from_flow_equals_pose_on_reference_points(engine):
+    """One fused submission == the reference's chain followed by computeP, image by image."""
+    hw = (120, 400)
+    B = 3
+    scs, flow, Kinv = _flow_batch(hw, B, seed=20)
+    tf, tk = dev(flow, torch.float32), dev(Kinv, torch.float32)
+    P32, E32, r = engine.pose_from_flow(tf, tk, 2, THR, margin=10)
+    assert P32.dtype == torch.float32 and P32.shape == (B, 3, 4) and E32.shape == (B, 3, 3)
+    assert torch.equal(E32, r.E.float()) and torch.equal(P32, r.P.float())
+    for b in range(B):
+        oa, oc = oracle.flow_to_points(flow[b], Kinv[b], 10)
+        one = engine.compute_pose(dev(oa), dev(oc), 2, THR)
+        assert one.count == r.count[b] and one.best_set == r.best_set[b]
+        assert torch.equal(one.E, r.E[b]) and torch.equal(one.P, r.P[b])
+        Pn = r.P[b].cpu().numpy()
+        assert synth.rotation_error_deg(Pn[:, :3], scs[b]["R"]) < 0.05       # degrees, vs ground truth
+        assert synth.translation_error_deg(Pn[:, 3], scs[b]["t"]) < 1.0
+    # keypoint list (integer gather), ragged per image
+    rng = np.random.default_rng(1)
+    n = [500, 2000, 64]
+    pts = np.stack([rng.integers(10, hw[1] - 10, sum(n)), rng.integers(10, hw[0] - 10, sum(n))], 1).astype(np.int32)
+    off = np.concatenate([[0], np.cumsum(n)])
+    P32, E32, r = engine.pose_from_flow(tf, tk, 2, THR, pts=torch.from_numpy(pts), offsets=off)
+    for b in range(B):
+        oa, oc = oracle.flow_to_points(flow[b], Kinv[b], 10, pts[off[b]:off[b + 1]])
+        one = engine.compute_pose(dev(oa), dev(oc), 2, THR)
+        assert one.count == r.count[b] and torch.equal(one.E, r.E[b])

@@ -209,3 +209,41 @@ def test_optimise_improves_towards_ground_truth(gold_polish):
         d0 = synth.essential_distance(g[f"opt{case}_E0"], Egt)
         E = oracle.optimise(g[f"opt{case}_x1"], g[f"opt{case}_x2"], g[f"opt{case}_E0"], 1e-4, 1.0, 10)
         assert synth.essential_distance(E, Egt) < 0.25 * d0
+
+
+# ---------------------------------------------------------------------------------------------
+# flow -> correspondences: numpy oracle against the reference's torch chain (CPU tensors)
+# ---------------------------------------------------------------------------------------------
+def test_flow_to_points_oracle_equals_reference_torch_chain():
+    import torch
+    import ref_flow_torch as rf
+    rng = np.random.default_rng(5)
+    H, W = 48, 80
+    flow = rng.normal(0, 4, (2, 2, H, W)).astype(np.float32)
+    K2 = synth.KITTI_K * np.array([[0.2], [0.2], [1.0]])
+    Kinv = np.stack([np.linalg.inv(synth.KITTI_K), np.linalg.inv(K2)]).astype(np.float32)
+    tf, tk = torch.from_numpy(flow), torch.from_numpy(Kinv)
+    ulp = np.float64(np.finfo(np.float32).eps)
+    for b in range(2):
+        pts_i = np.stack([rng.integers(0, W, 40), rng.integers(0, H, 40)], 1)
+        pts_f = np.stack([rng.uniform(0, W - 1, 40), rng.uniform(0, H - 1, 40)], 1)
+        pts_f[0] = (W - 1, H - 1)                        # corner: three taps fall outside
+        for kw, opts in ((dict(), None), (dict(pts=pts_i.astype(np.float64)), pts_i),
+                         (dict(pts=pts_f, sample_sp=True), pts_f.astype(np.float32))):
+            a, c = rf.points_of_image(tf, tk, b, 10, **kw)
+            oa, oc = oracle.flow_to_points(flow[b], Kinv[b], 10, opts)
+            assert oa.shape == tuple(a.shape) and oa.dtype == np.float64
+            # float32 arithmetic on both sides; BLAS may order the 3-term sum differently: 1 ulp
+            assert np.abs(a.numpy() - oa).max() <= ulp * max(1.0, np.abs(oa).max())
+            assert np.abs(c.numpy() - oc).max() <= ulp * max(1.0, np.abs(oc).max())
+    n = (H - 20) * (W - 20)
+    assert oracle.flow_to_points(flow[0], Kinv[0], 10)[0].shape == (n, 2)
+
+
+def test_flow_scene_recovers_pose_through_oracle():
+    sc = synth.make_flow(hw=(60, 200), seed=3)
+    x1, x2 = oracle.flow_to_points(sc["flow"], sc["Kinv"], 10)
+    sets = synth.make_sets(x1.shape[0], 512, 11)
+    r = oracle.ransac(x1, x2, sets, 1, 1e-4)
+    assert synth.rotation_error_deg(r["P"][:, :3], sc["R"]) < 0.05
+    assert r["count"] > 0.6 * x1.shape[0]
