@@ -363,6 +363,45 @@ def run_ours(args):
     torch.cuda.synchronize()
     single_ms = e0.elapsed_time(e1) / 50
 
+    # ---- the kernels either side of the path, outside the timed region
+    def timed(fn, reps=20, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    other = {}
+    try:
+        Hh, Ww = synth.KITTI_HW
+        Bf = 16                                   # 16 dense KITTI frames: 290 MB of traffic > L2
+        flow = torch.randn(Bf, 2, Hh, Ww, device=dev) * 3.0
+        Kinv = torch.from_numpy(np.linalg.inv(synth.KITTI_K).astype(np.float32)).to(dev).repeat(Bf, 1, 1)
+        ms_f = timed(lambda: eng.flow_to_points(flow, Kinv, 10))
+        n_pts = Bf * (Hh - 20) * (Ww - 20)
+        bytes_f = n_pts * (8 + 32)                # 2 float32 read + 2 double2 written per correspondence
+        hbm_peak = roof.get("hbm_gbs_measured_peak") or 6555.8
+        other["flow_points"] = {"bound": "hbm", "ms": ms_f, "correspondences": n_pts,
+                                "achieved": bytes_f / (ms_f * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": bytes_f / (ms_f * 1e-3) * 1e-9 / hbm_peak,
+                                "algorithmic_bytes_per_correspondence": 40,
+                                "workload": f"{Bf} dense 370x1226 frames, margin 10 (models/SFMnet.py:239-263 chain)"}
+        # the same chain + pose for one dense frame (config 4 shape at 4096 hypotheses)
+        ms_pf = timed(lambda: eng.pose_from_flow(flow[:1], Kinv[:1], ITERS, THR), reps=5, warm=2)
+        other["pose_from_flow_dense_frame"] = {"ms": ms_pf, "correspondences": n_pts // Bf, "n_hyp": H}
+        # IRLS refinement (essential_matrix.optimise), 10 Gauss-Newton updates per problem
+        E0 = Eo[:B].clone()
+        ms_o = timed(lambda: eng.optimise_batch(x1, x2, off, E0, THR, 1.0, 10), reps=5, warm=2)
+        ms_o1 = timed(lambda: eng.optimise(a, b, E0[0], THR, 1.0, 10), reps=20, warm=3)
+        other["irls_polish"] = {"batch_ms": ms_o, "problems": B, "points_each": N_CORR, "updates": 10,
+                                "problems_per_s": B / (ms_o * 1e-3), "single_problem_ms": ms_o1}
+    except Exception as ex:  # never lose the headline line to an auxiliary measurement
+        other["error"] = repr(ex)
+
     # accuracy of the batch against ground truth
     Pn = Po[:B].cpu().numpy()
     rot = [synth.rotation_error_deg(Pn[i][:, :3], pairs[i]["R"]) for i in range(B)]
@@ -375,10 +414,11 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "tv5_compute_pose_batch_host (C ABI, pinned host buffers)"},
-            "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "gpu_launches": KERNELS_PER_STEP * eng.pipeline_chunks(B) * args.steps,
             "roofline": roof,
             "stage_ms_per_step": stage_ms,
             "single_pair_latency_ms": single_ms,
+            "other_kernels": other,
             "fp32_peak_tflops": {"ffma": peak_ffma, "ffma2": peak_ffma2, "nominal": nominal},
             "hypotheses_per_pair": M_total / B,
             "candidates_per_pair": float(so_h[:B, 4].mean()),

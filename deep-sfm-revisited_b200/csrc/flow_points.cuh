@@ -53,9 +53,11 @@ __global__ void __launch_bounds__(256) flow_points(const FlowJob* __restrict__ j
   float a0, a1, a2, b0, b1, b2;  // homogeneous pixel coordinates in image 1 / image 2
   if (mode == kFlowBilinear) {
     const float2 p = __ldg(reinterpret_cast<const float2*>(J.pts) + k);
-    // the reference normalises to [-1,1] (SFMnet.py:247) and grid_sample maps back
-    const float gx = 2.0f * p.x / (float)max(W - 1, 1) - 1.0f;
-    const float gy = 2.0f * p.y / (float)max(H - 1, 1) - 1.0f;
+    // the reference normalises to [-1,1] with separate torch ops on the GPU (SFMnet.py:247) and
+    // grid_sample maps back; torch's CUDA division by a Python scalar multiplies by the
+    // reciprocal, and nothing is fused across the three ops
+    const float gx = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, p.x), __frcp_rn((float)max(W - 1, 1))), 1.0f);
+    const float gy = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, p.y), __frcp_rn((float)max(H - 1, 1))), 1.0f);
     const float ix = ((gx + 1.0f) / 2.0f) * (float)(W - 1);
     const float iy = ((gy + 1.0f) / 2.0f) * (float)(H - 1);
     const float x0f = floorf(ix), y0f = floorf(iy);

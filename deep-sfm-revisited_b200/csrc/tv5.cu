@@ -771,7 +771,7 @@ static int ensure_workspace(tv5_ctx* ctx, int B, size_t total_pp, size_t total_s
     if ((rc = grow_same(ctx, w.state, w.desc_cap, nc))) return rc;
     w.desc_cap = nc;
   }
-  if (!w.ctl && cudaMalloc(&w.ctl, sizeof(Control)) != cudaSuccess) return TV5_ERR_NOMEM;
+  if (!w.ctl && cudaMalloc(&w.ctl, sizeof(Control) * kPipeChunks) != cudaSuccess) return TV5_ERR_NOMEM;
   if ((rc = grow(ctx, w.pp, w.pp_cap, total_pp))) return rc;
   if (total_sets > w.sets_cap || !w.E_list) {
     size_t nc = std::max(total_sets, w.sets_cap + w.sets_cap / 2);
@@ -795,8 +795,51 @@ static void stage_mark(tv5_ctx* ctx, cudaStream_t st, int i) {
   if (ctx->profiling) cudaEventRecord(ctx->ev[i], st);
 }
 
+// profiling events of the pose pipeline: kProfPerChunk per chunk
+//   0 prep start, 1 solve start, 2 solve end (front stream)
+//   3 plan start, 4 score start, 5 score end, 6 finalize start, 7 finalize end (back stream)
+static int ensure_prof_events(tv5_ctx* ctx, int n_chunks) {
+  while ((int)ctx->prof_ev.size() < n_chunks * kProfPerChunk) {
+    cudaEvent_t e;
+    TV5_CUDA(ctx, cudaEventCreate(&e));
+    ctx->prof_ev.push_back(e);
+  }
+  return TV5_OK;
+}
+
+static int ensure_pipe_streams(tv5_ctx* ctx) {
+  if (ctx->front_stream) return TV5_OK;
+  int lo = 0, hi = 0;
+  TV5_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least priority (numerically largest)
+  TV5_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->back_stream, cudaStreamNonBlocking, hi));
+  TV5_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->front_stream, cudaStreamNonBlocking, lo));
+  TV5_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_entry, cudaEventDisableTiming));
+  TV5_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_done, cudaEventDisableTiming));
+  for (auto& e : ctx->pipe_solved) TV5_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return TV5_OK;
+}
+
 static void profile_collect(tv5_ctx* ctx) {
   if (!ctx->profiling || !ctx->ev_pending) return;
+  ctx->ev_pending = false;
+  if (ctx->prof_chunks > 0) {  // pose pipeline
+    static const int kFrom[TV5_N_STAGES] = {0, 1, 3, 4, 5, 6};
+    static const int kTo[TV5_N_STAGES] = {1, 2, 4, 5, 6, 7};
+    cudaEventSynchronize(ctx->prof_ev[(ctx->prof_chunks - 1) * kProfPerChunk + 7]);
+    for (int i = 0; i < TV5_N_STAGES; ++i) {
+      double sum = 0.0;
+      bool ok = true;
+      for (int c = 0; c < ctx->prof_chunks; ++c) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->prof_ev[c * kProfPerChunk + kFrom[i]],
+                                 ctx->prof_ev[c * kProfPerChunk + kTo[i]]) != cudaSuccess) { ok = false; break; }
+        sum += ms;
+      }
+      if (ok) { ctx->stage_ms[i] += sum; ctx->stage_launches[i] += 1; }
+    }
+    ctx->prof_chunks = 0;
+    return;
+  }
   cudaEventSynchronize(ctx->ev[TV5_N_STAGES]);
   for (int i = 0; i < TV5_N_STAGES; ++i) {
     float ms = 0.f;
@@ -805,7 +848,6 @@ static void profile_collect(tv5_ctx* ctx) {
       ctx->stage_launches[i] += 1;
     }
   }
-  ctx->ev_pending = false;
 }
 
 extern "C" {
@@ -882,6 +924,14 @@ int tv5_destroy(tv5_ctx* ctx) {
   }
   for (int i = 0; i <= TV5_N_STAGES; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (auto e : ctx->prof_ev) cudaEventDestroy(e);
+  if (ctx->front_stream) {
+    cudaStreamDestroy(ctx->front_stream);
+    cudaStreamDestroy(ctx->back_stream);
+    cudaEventDestroy(ctx->pipe_entry);
+    cudaEventDestroy(ctx->pipe_done);
+    for (auto& e : ctx->pipe_solved) cudaEventDestroy(e);
+  }
   delete ctx;
   return TV5_OK;
 }
@@ -919,10 +969,13 @@ static int cached_rng_table(tv5_ctx* ctx, cudaStream_t st, int N, int iters, con
   return TV5_OK;
 }
 
-int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, const double* x2,
+// ready_ev / ready_first (optional): input chunk k = pairs [ready_first[k], ready_first[k+1]) is
+// complete in device memory once ready_ev[k] has fired (host-buffer entry point).
+static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, const double* x2,
                            const int64_t* pt_offsets, const int32_t* sets, int iters, int n_pre,
                            int n_full, double thr, int with_cheirality, double* E_out,
-                           double* P_out, tv5_result* result, uint8_t* mask_out) {
+                           double* P_out, tv5_result* result, uint8_t* mask_out,
+                           const cudaEvent_t* ready_ev, const int* ready_first, int n_ready) {
   if (!ctx || B < 1 || !x1 || !x2 || !pt_offsets || iters < 1 || !E_out || !result) return TV5_ERR_INVALID;
   if (!(thr > 0.0) || !(thr < 1e300)) return TV5_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
@@ -968,60 +1021,145 @@ int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, 
   TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState) * B, st));
   const int allow_fast = (two_stage || ctx->force_exact) ? 0 : 1;
 
-  stage_mark(ctx, st, 0);
-  prep_norms<<<dim3((max_pp + 255) / 256, B), 256, 0, st>>>(w.desc, w.state);
-  band_consts<<<(B + 127) / 128, 128, 0, st>>>(w.desc, w.state, B, thr, allow_fast);
-  if (allow_fast) prep_points<<<dim3((max_pp + 255) / 256, B), 256, 0, st>>>(w.desc, w.state, w.pp);
-  stage_mark(ctx, st, 1);
-  solve_sets<<<dim3((H + 31) / 32, B), 32, 0, st>>>(w.desc, w.state, H, with_cheirality, w.E_list,
-                                                   with_cheirality ? w.P_list : nullptr, w.n_valid,
-                                                   w.n_roots, w.hyp, w.hyp_id, w.notin, w.out);
-  stage_mark(ctx, st, 2);
-  // tile size: big tiles for batches, enough tiles to balance 2 CTAs/SM for a single pair
+  // A submission may be cut into chunks of pairs, each with a front (prep + five-point solve:
+  // float64, latency bound) and a back (scoring: float32 pipe bound, + selection).
+  //  * host-buffer entry point: chunk c runs as soon as its copies have landed (ready_ev), in
+  //    plain order front(c), back(c) on the caller's stream;
+  //  * tv5_set_overlap(1): fronts on a low-priority and backs on a high-priority internal stream,
+  //    so the solver of chunk c+1 runs in the shadow of the scorer of chunk c.  Measured on B200
+  //    (DESIGN.md section 4.4): no gain — solver warps make almost no progress next to the
+  //    FFMA2-saturating scorer — hence off by default.
+  int n_chunks = 1;
+  if ((ctx->overlap || ready_ev) && !two_stage) n_chunks = std::max(1, std::min(kPipeChunks, B / kPipeMinPairs));
+  const bool two_streams = ctx->overlap && n_chunks > 1;
+  cudaStream_t s_front = st, s_back = st;
+  if (two_streams) {
+    if ((rc = ensure_pipe_streams(ctx))) return rc;
+    s_front = ctx->front_stream;
+    s_back = ctx->back_stream;
+    TV5_CUDA(ctx, cudaEventRecord(ctx->pipe_entry, st));
+    TV5_CUDA(ctx, cudaStreamWaitEvent(s_front, ctx->pipe_entry, 0));
+    TV5_CUDA(ctx, cudaStreamWaitEvent(s_back, ctx->pipe_entry, 0));
+  }
+  std::vector<int> first((size_t)n_chunks + 1);
+  for (int c = 0; c <= n_chunks; ++c) first[c] = (int)((int64_t)B * c / n_chunks);
   const int slots = TV5_SCORE_MINB * ctx->sm_count;
-  int pp_per_tile = kMaxTilePairs;
-  {
-    const double est_M = (double)H * (with_cheirality ? 3.0 : 4.5);
-    const double n_hc = std::max(1.0, est_M / kHypChunk);
-    const double want_pc = 6.0 * slots / (n_hc * B);
-    if (want_pc > 1.0) {
-      int t = (int)((double)max_pp / want_pc);
-      t = (t + 7) & ~7;
-      pp_per_tile = std::max(64, std::min(kMaxTilePairs, t));
+  const bool prof = ctx->profiling;
+  if (prof && (rc = ensure_prof_events(ctx, n_chunks))) return rc;
+  ctx->prof_chunks = prof ? n_chunks : 0;
+
+  // ---- front: prep + solve of one chunk
+  auto front = [&](int c) -> int {
+    const int b0 = first[c], nb = first[c + 1] - b0;
+    int cmax_pp = 0;
+    for (int b = b0; b < b0 + nb; ++b) cmax_pp = std::max(cmax_pp, (hd[b].n + 1) / 2);
+    const PairDesc* desc = w.desc + b0;
+    PairState* state = w.state + b0;
+    const size_t so = (size_t)b0 * H;
+    if (ready_ev) {  // inputs of this chunk: every host chunk up to the one holding its last pair
+      int k = 0;
+      while (k + 1 < n_ready && ready_first[k + 1] < b0 + nb) ++k;
+      for (int j = (c == 0 ? 0 : k); j <= k; ++j) TV5_CUDA(ctx, cudaStreamWaitEvent(s_front, ready_ev[j], 0));
     }
-  }
-  plan_tiles<<<1, 1024, 0, st>>>(w.desc, w.state, w.ctl, B, pp_per_tile);
-  stage_mark(ctx, st, 3);
-  if (allow_fast)
-    score_bounds<false><<<slots, kScoreThreads, 0, st>>>(w.desc, w.state, w.ctl, B, H, pp_per_tile, w.pp,
-                                                         w.hyp, w.notin, w.out);
-  stage_mark(ctx, st, 4);
-  const int X = std::max(1, std::min(4096, (4 * ctx->sm_count + B - 1) / B));
-  pick_top<<<B, 256, 0, st>>>(w.desc, w.state, H, w.out, w.hyp_id, w.cand, w.cand_cnt);
-  if (two_stage) {
-    // stage A runs on n_pre points: exact_counts reads n_full, so the descriptors are
-    // re-uploaded with n_full := n_pre for this stage and restored afterwards.
-    std::vector<PairDesc> ha = hd;
-    for (auto& d : ha) d.n_full = d.n_pre;
-    TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, ha.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, st));
-    exact_counts<<<dim3(X, B), 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, w.hyp_id, w.cand, w.cand_cnt);
-    set_winners<<<B, 256, 0, st>>>(w.desc, w.state, H, w.hyp_id, w.cand, w.cand_cnt, w.cand + w.sets_cap * 10);
-    TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, hd.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, st));
-    exact_counts<<<dim3(X, B), 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, w.hyp_id, w.cand, w.cand_cnt);
+    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 0], s_front);
+    prep_norms<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_front>>>(desc, state);
+    band_consts<<<(nb + 127) / 128, 128, 0, s_front>>>(desc, state, nb, thr, allow_fast);
+    if (allow_fast) prep_points<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_front>>>(desc, state, w.pp);
+    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 1], s_front);
+    solve_sets<<<dim3((H + 31) / 32, nb), 32, 0, s_front>>>(
+        desc, state, H, with_cheirality, w.E_list + so * 90, with_cheirality ? w.P_list + so * 120 : nullptr,
+        w.n_valid + so, w.n_roots + so, w.hyp + so * 10, w.hyp_id + so * 10, w.notin + so * 10, w.out + so * 10);
+    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 2], s_front);
+    if (two_streams) TV5_CUDA(ctx, cudaEventRecord(ctx->pipe_solved[c], s_front));
+    return TV5_OK;
+  };
+  // ---- back: scoring + selection of one chunk
+  auto back = [&](int c) -> int {
+    const int b0 = first[c], nb = first[c + 1] - b0;
+    int cmax_pp = 0;
+    for (int b = b0; b < b0 + nb; ++b) cmax_pp = std::max(cmax_pp, (hd[b].n + 1) / 2);
+    PairDesc* desc = w.desc + b0;
+    PairState* state = w.state + b0;
+    Control* ctl = w.ctl + c;
+    const size_t so = (size_t)b0 * H;
+    const double* E_list = w.E_list + so * 90;
+    const double* P_list = with_cheirality ? w.P_list + so * 120 : nullptr;
+    const Hyp32* hyp = w.hyp + so * 10;
+    int32_t* hyp_id = w.hyp_id + so * 10;
+    uint32_t* notin = w.notin + so * 10;
+    uint32_t* out = w.out + so * 10;
+    int32_t* cand = w.cand + so * 10;
+    int32_t* cand_cnt = w.cand_cnt + so * 10;
+    if (two_streams) TV5_CUDA(ctx, cudaStreamWaitEvent(s_back, ctx->pipe_solved[c], 0));
+    // tile size: big tiles for batches, enough tiles to balance 2 CTAs/SM for a single pair
+    int pp_per_tile = kMaxTilePairs;
+    {
+      const double est_M = (double)H * (with_cheirality ? 3.0 : 4.5);
+      const double n_hc = std::max(1.0, est_M / kHypChunk);
+      const double want_pc = 6.0 * slots / (n_hc * nb);
+      if (want_pc > 1.0) {
+        int t = (int)((double)cmax_pp / want_pc);
+        t = (t + 7) & ~7;
+        pp_per_tile = std::max(64, std::min(kMaxTilePairs, t));
+      }
+    }
+    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 3], s_back);
+    plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile);
+    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 4], s_back);
+    if (allow_fast)
+      score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
+                                                              notin, out);
+    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 5], s_back);
+    const int X = std::max(1, std::min(4096, (4 * ctx->sm_count + nb - 1) / nb));
+    pick_top<<<nb, 256, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
+    if (two_stage) {
+      // (single chunk) stage A runs on n_pre points: exact_counts reads n_full, so the descriptors
+      // are re-uploaded with n_full := n_pre for this stage and restored afterwards.
+      std::vector<PairDesc> ha = hd;
+      for (auto& d : ha) d.n_full = d.n_pre;
+      TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, ha.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, s_back));
+      exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
+      set_winners<<<nb, 256, 0, s_back>>>(desc, state, H, hyp_id, cand, cand_cnt, w.cand + w.sets_cap * 10);
+      TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, hd.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, s_back));
+      exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
+    } else {
+      exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
+      if (allow_fast) {
+        pick_rest<<<nb, 256, 0, s_back>>>(desc, state, H, out, cand, cand_cnt);
+        exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
+      }
+    }
+    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 6], s_back);
+    finalize<<<nb, 256, 0, s_back>>>(desc, state, H, thr, E_list, P_list, hyp_id, cand, cand_cnt);
+    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 7], s_back);
+    return TV5_OK;
+  };
+  if (two_streams) {
+    for (int c = 0; c < n_chunks; ++c)
+      if ((rc = front(c))) return rc;
+    for (int c = 0; c < n_chunks; ++c)
+      if ((rc = back(c))) return rc;
   } else {
-    exact_counts<<<dim3(X, B), 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, w.hyp_id, w.cand, w.cand_cnt);
-    if (allow_fast) {
-      pick_rest<<<B, 256, 0, st>>>(w.desc, w.state, H, w.out, w.cand, w.cand_cnt);
-      exact_counts<<<dim3(X, B), 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, w.hyp_id, w.cand, w.cand_cnt);
+    for (int c = 0; c < n_chunks; ++c) {
+      if ((rc = front(c))) return rc;
+      if ((rc = back(c))) return rc;
     }
   }
-  stage_mark(ctx, st, 5);
-  finalize<<<B, 256, 0, st>>>(w.desc, w.state, H, thr, w.E_list, with_cheirality ? w.P_list : nullptr,
-                              w.hyp_id, w.cand, w.cand_cnt);
-  stage_mark(ctx, st, 6);
-  if (ctx->profiling) ctx->ev_pending = true;
+  if (two_streams) {
+    TV5_CUDA(ctx, cudaEventRecord(ctx->pipe_done, s_back));
+    TV5_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_done, 0));
+  }
+  if (prof) ctx->ev_pending = true;
   TV5_CUDA(ctx, cudaGetLastError());
   return TV5_OK;
+}
+
+int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, const double* x2,
+                           const int64_t* pt_offsets, const int32_t* sets, int iters, int n_pre,
+                           int n_full, double thr, int with_cheirality, double* E_out,
+                           double* P_out, tv5_result* result, uint8_t* mask_out) {
+  return pose_batch_impl(ctx, stream, B, x1, x2, pt_offsets, sets, iters, n_pre, n_full, thr, with_cheirality,
+                         E_out, P_out, result, mask_out, nullptr, nullptr, 0);
 }
 
 int tv5_compute_pose(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
@@ -1080,19 +1218,12 @@ int tv5_compute_pose_batch_host(tv5_ctx* ctx, void* stream, int B, const double*
                                     ctx->copy_stream));
     TV5_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[k], ctx->copy_stream));
   }
-  std::vector<int64_t> off;
-  for (int k = 0; k < n_chunks; ++k) {
-    const int b0 = first[k], b1 = first[k + 1];
-    off.assign((size_t)(b1 - b0) + 1, 0);
-    for (int b = b0; b <= b1; ++b) off[b - b0] = pt_offsets[b] - pt_offsets[b0];
-    const size_t p0 = (size_t)(pt_offsets[b0] - pt_offsets[0]);
-    TV5_CUDA(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
-    rc = tv5_compute_pose_batch(ctx, stream, b1 - b0, dx1 + 2 * p0, dx2 + 2 * p0, off.data(),
-                                sets ? w.h2d_sets + (size_t)b0 * H * 5 : nullptr, iters, n_pre, n_full, thr,
-                                with_cheirality, w.out_E + 9 * (size_t)b0, w.out_P + 12 * (size_t)b0,
-                                w.out_res + b0, nullptr);
-    if (rc) return rc;
-  }
+  // one submission; each chunk of pairs starts as soon as its copies have landed
+  std::vector<int64_t> off((size_t)B + 1);
+  for (int b = 0; b <= B; ++b) off[b] = pt_offsets[b] - pt_offsets[0];
+  rc = pose_batch_impl(ctx, stream, B, dx1, dx2, off.data(), sets ? w.h2d_sets : nullptr, iters, n_pre, n_full, thr,
+                       with_cheirality, w.out_E, w.out_P, w.out_res, nullptr, ctx->chunk_ev, first.data(), n_chunks);
+  if (rc) return rc;
   TV5_CUDA(ctx, cudaMemcpyAsync(E_out, w.out_E, (size_t)B * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (P_out) TV5_CUDA(ctx, cudaMemcpyAsync(P_out, w.out_P, (size_t)B * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TV5_CUDA(ctx, cudaMemcpyAsync(result, w.out_res, (size_t)B * sizeof(tv5_result), cudaMemcpyDeviceToHost, st));
@@ -1428,6 +1559,12 @@ int tv5_measure_fp32_peak(tv5_ctx* ctx, int mode, double* tflops_out) {
 int tv5_set_force_exact(tv5_ctx* ctx, int on) {
   if (!ctx) return TV5_ERR_INVALID;
   ctx->force_exact = on != 0;
+  return TV5_OK;
+}
+
+int tv5_set_overlap(tv5_ctx* ctx, int on) {
+  if (!ctx) return TV5_ERR_INVALID;
+  ctx->overlap = on != 0;
   return TV5_OK;
 }
 

@@ -29,6 +29,9 @@ constexpr int kScoreUnroll = TV5_SCORE_UNROLL;
 constexpr int kMaxTilePairs = 512;   // point pairs staged in shared memory per tile (24 KB)
 constexpr int kExactChunk = 2048;    // points per work item of the float64 scorer
 constexpr int kHostChunks = 8;       // pipeline depth of the host-buffer entry point
+constexpr int kPipeChunks = 8;       // chunks of pairs of one submission (solver / scorer overlap)
+constexpr int kPipeMinPairs = 16;    // ... each at least this many pairs
+constexpr int kProfPerChunk = 8;     // profiling events per chunk
 
 // Per image pair: geometry of the job (written by the host) ...
 struct PairDesc {
@@ -118,4 +121,13 @@ struct tv5_ctx {
   cudaEvent_t chunk_ev[tv5::kHostChunks] = {};
   cudaEvent_t start_ev = nullptr;
   int polish_max_ctas = 0;              // co-resident CTAs of irls_polish on this device
+  // solver / scorer overlap inside one submission
+  bool overlap = false;
+  bool profiling_serial = false;
+  cudaStream_t front_stream = nullptr;  // prep + solve, least priority
+  cudaStream_t back_stream = nullptr;   // scoring + selection, highest priority
+  cudaEvent_t pipe_entry = nullptr, pipe_done = nullptr;
+  cudaEvent_t pipe_solved[tv5::kPipeChunks] = {};
+  std::vector<cudaEvent_t> prof_ev;
+  int prof_chunks = 0;
 };

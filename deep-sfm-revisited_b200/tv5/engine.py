@@ -397,6 +397,15 @@ class Engine:
     def set_force_exact(self, on=True):
         _check(self.ctx, self.L.tv5_set_force_exact(self.ctx, int(bool(on))), "set_force_exact")
 
+    def set_overlap(self, on=True):
+        """Solver/scorer overlap inside one submission (default off); results do not depend on it."""
+        _check(self.ctx, self.L.tv5_set_overlap(self.ctx, int(bool(on))), "set_overlap")
+        self.overlap = bool(on)
+
+    def pipeline_chunks(self, B):
+        """Chunks a submission of B pairs is cut into (tv5_internal.h: kPipeChunks, kPipeMinPairs)."""
+        return max(1, min(8, int(B) // 16)) if getattr(self, "overlap", False) else 1
+
     def profile_enable(self, on=True):
         _check(self.ctx, self.L.tv5_profile_enable(self.ctx, int(bool(on))), "profile_enable")
 

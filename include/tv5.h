@@ -241,6 +241,12 @@ int tv5_pose_from_flow(tv5_ctx* ctx, void* stream, const float* flow, int B, int
  * tests use this to prove it. */
 int tv5_set_force_exact(tv5_ctx* ctx, int on);
 
+/* Solver/scorer overlap (experimental, default off): a submission of >= 32 pairs is cut into up
+ * to 8 chunks whose five-point solve runs on a low-priority internal stream concurrently with the
+ * scoring of the previous chunk on a high-priority one; results are identical either way.
+ * Measured on B200: no throughput gain. */
+int tv5_set_overlap(tv5_ctx* ctx, int on);
+
 /* Device-timed (CUDA events) measurements used by bench.py; both synchronise. */
 
 /* FP32 FMA-chain peak of this GPU in TFLOP/s: mode 0 = scalar FFMA, 1 = packed FFMA2. */

@@ -230,7 +230,7 @@ def ref_solve_sets(x1, x2, sets):
 # ---------------------------------------------------------------------------------------------
 # optical flow -> normalised correspondences (front of pose_by_ransac), numpy float32
 # ---------------------------------------------------------------------------------------------
-def flow_to_points(flow, Kinv, margin=10, pts=None):
+def flow_to_points(flow, Kinv, margin=10, pts=None, cuda_division=True):
     """One image.  flow [2,H,W] float32, Kinv [3,3] float32 -> x1, x2 [n,2] float64.
 
     Restates, in float32 like the reference, flow2coord (models/SFMnet.py:298-318: pixel grid,
@@ -239,7 +239,9 @@ def flow_to_points(flow, Kinv, margin=10, pts=None):
     align_corners=True and zero padding :244-249 for a float list), bmm(K^-1, .) (:259-260),
     the [:, :2] slice (:262-263) and .double() (epipolar_utils.py:130).  The three-term
     products with K^-1 are accumulated k = 0, 1, 2 with fused multiply-adds like an SGEMM inner
-    loop (emulated exactly in float64: a float32 product is exact there)."""
+    loop (emulated exactly in float64: a float32 product is exact there).
+    cuda_division: torch divides a CUDA tensor by a Python scalar as x * (1/s) (the reference always
+    runs this chain on the GPU); False gives torch's CPU behaviour x / s."""
     f32 = np.float32
     flow = np.asarray(flow, dtype=f32)
     K = np.asarray(Kinv, dtype=f32)
@@ -256,8 +258,12 @@ def flow_to_points(flow, Kinv, margin=10, pts=None):
         a, b = c1[:, p[:, 1], p[:, 0]], c2[:, p[:, 1], p[:, 0]]
     else:
         p = np.asarray(pts, dtype=f32)
-        gxn = f32(2.0) * p[:, 0] / f32(max(W - 1, 1)) - f32(1.0)
-        gyn = f32(2.0) * p[:, 1] / f32(max(H - 1, 1)) - f32(1.0)
+        if cuda_division:
+            gxn = (f32(2.0) * p[:, 0]) * (f32(1.0) / f32(max(W - 1, 1))) - f32(1.0)
+            gyn = (f32(2.0) * p[:, 1]) * (f32(1.0) / f32(max(H - 1, 1))) - f32(1.0)
+        else:
+            gxn = f32(2.0) * p[:, 0] / f32(max(W - 1, 1)) - f32(1.0)
+            gyn = f32(2.0) * p[:, 1] / f32(max(H - 1, 1)) - f32(1.0)
         ix = ((gxn + f32(1.0)) / f32(2.0)) * f32(W - 1)
         iy = ((gyn + f32(1.0)) / f32(2.0)) * f32(H - 1)
         x0, y0 = np.floor(ix), np.floor(iy)

@@ -509,6 +509,10 @@ def test_flow_to_points_matches_oracle_and_reference_torch_chain(engine, hw):
                                          else dict(pts=p.astype(np.float64), sample_sp=True))
             ta, tc = rf.points_of_image(tf, tk, b, 10, **kw)
             tol = ulp * max(1.0, np.abs(oc).max())
+            if name == "bilinear":
+                # torch's CUDA grid_sample may round its four-tap sums differently (no documented
+                # operation order): allow 4 ulp of the pixel coordinate (<= W) scaled by K^-1
+                tol = max(tol, 4 * ulp * W * float(np.abs(Kinv[b][0, 0])))
             assert np.abs(ma - ta.cpu().numpy()).max() <= tol, name
             assert np.abs(mc - tc.cpu().numpy()).max() <= tol, name
 

@@ -231,7 +231,7 @@ def test_flow_to_points_oracle_equals_reference_torch_chain():
         for kw, opts in ((dict(), None), (dict(pts=pts_i.astype(np.float64)), pts_i),
                          (dict(pts=pts_f, sample_sp=True), pts_f.astype(np.float32))):
             a, c = rf.points_of_image(tf, tk, b, 10, **kw)
-            oa, oc = oracle.flow_to_points(flow[b], Kinv[b], 10, opts)
+            oa, oc = oracle.flow_to_points(flow[b], Kinv[b], 10, opts, cuda_division=False)  # CPU torch
             assert oa.shape == tuple(a.shape) and oa.dtype == np.float64
             # float32 arithmetic on both sides; BLAS may order the 3-term sum differently: 1 ulp
             assert np.abs(a.numpy() - oa).max() <= ulp * max(1.0, np.abs(oa).max())
