@@ -399,6 +399,24 @@ def run_ours(args):
         ms_o1 = timed(lambda: eng.optimise(a, b, E0[0], THR, 1.0, 10), reps=20, warm=3)
         other["irls_polish"] = {"batch_ms": ms_o, "problems": B, "points_each": N_CORR, "updates": 10,
                                 "problems_per_s": B / (ms_o * 1e-3), "single_problem_ms": ms_o1}
+        # plane-sweep cost volume (consumer of P): PSNet's shape, nlabel = 128, b = 1 (configs[4])
+        Cc, hq, wq, L = 32, (Hh + 3) // 4, (Ww + 3) // 4, 128
+        rf = torch.randn(1, Cc, hq, wq, device=dev)
+        tg = torch.randn(1, Cc, hq, wq, device=dev)
+        Kq = synth.KITTI_K.copy()
+        Kq[:2] /= 4.0
+        K4 = torch.from_numpy(Kq.astype(np.float32)).to(dev)[None]
+        Ki4 = torch.from_numpy(np.linalg.inv(Kq).astype(np.float32)).to(dev)[None]
+        P32 = Po[:1].float()
+        vol = torch.empty(1, 2 * Cc, L, hq, wq, device=dev)
+        ms_s = timed(lambda: eng.plane_sweep(rf, tg, P32, K4, Ki4, L, 1.0, out=vol), reps=10, warm=3)
+        bytes_s = vol.numel() * 4 + 2 * rf.numel() * 4
+        other["plane_sweep"] = {"bound": "hbm", "ms": ms_s, "achieved": bytes_s / (ms_s * 1e-3) * 1e-9,
+                                "peak": hbm_peak, "unit": "GB/s", "frac": bytes_s / (ms_s * 1e-3) * 1e-9 / hbm_peak,
+                                "algorithmic_bytes_per_launch": bytes_s,
+                                "workload": f"b=1, {Cc} channels, {hq}x{wq} features, nlabel {L} "
+                                            "(models/PSNet.py:141-157 loop; volume written once, 922 MB)"}
+        del vol
     except Exception as ex:  # never lose the headline line to an auxiliary measurement
         other["error"] = repr(ex)
 

@@ -25,6 +25,7 @@
 #include "solve5_coop.cuh"
 #include "polish.cuh"
 #include "flow_points.cuh"
+#include "plane_sweep.cuh"
 #include "tv5_internal.h"
 
 namespace tv5 {
@@ -1524,6 +1525,24 @@ int tv5_pose_from_flow(tv5_ctx* ctx, void* stream, const float* flow, int B, int
     pose_to_float<<<(B * 12 + 127) / 128, 128, 0, st>>>(E64, P64, B, E32_out, P32_out);
     TV5_CUDA(ctx, cudaGetLastError());
   }
+  return TV5_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// plane-sweep cost volume (plane_sweep.cuh)
+// ------------------------------------------------------------------------------------------
+int tv5_plane_sweep(tv5_ctx* ctx, void* stream, const float* ref_feat, const float* tgt_feat,
+                    const float* pose, const float* K, const float* Kinv, int B, int C, int h, int w,
+                    int nlabel, float mindepth, int by_depth, float* cost) {
+  if (!ctx || !ref_feat || !tgt_feat || !pose || !K || !Kinv || !cost) return TV5_ERR_INVALID;
+  if (B < 1 || C < 1 || h < 2 || w < 2 || nlabel < 1 || B > 65535 || nlabel > 65535) return TV5_ERR_INVALID;
+  if ((int64_t)h * w > 0x3fffffff) return TV5_ERR_INVALID;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  SweepParams P;
+  P.ref = ref_feat; P.tgt = tgt_feat; P.pose = pose; P.K = K; P.Kinv = Kinv; P.cost = cost;
+  P.C = C; P.h = h; P.w = w; P.L = nlabel; P.mindepth = mindepth; P.by_depth = by_depth ? 1 : 0;
+  plane_sweep<<<dim3((unsigned)((h * w + 255) / 256), nlabel, B), 256, 0, (cudaStream_t)stream>>>(P);
+  TV5_CUDA(ctx, cudaGetLastError());
   return TV5_OK;
 }
 

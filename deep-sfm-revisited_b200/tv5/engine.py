@@ -314,6 +314,35 @@ class Engine:
         _check(self.ctx, rc, "tv5_pose_from_flow")
         return P32, E32, PoseResult(E, P, stats)
 
+    # -- plane-sweep cost volume (consumer of P: models/PSNet.py:141-157) -----------------------
+    def plane_sweep(self, ref_fea, tgt_fea, pose, intrinsics4, intrinsics_inv4, nlabel, mindepth=1.0,
+                    by_depth=False, out=None):
+        """ref_fea, tgt_fea [B,C,h,w] f32; pose [B,3,4]; intrinsics at feature resolution [B,3,3]
+        -> cost [B,2C,nlabel,h,w] f32 (what PSNet.forward builds before its 3-D convolutions)."""
+        for t, name in ((ref_fea, "ref_fea"), (tgt_fea, "tgt_fea")):
+            if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or t.dim() != 4:
+                raise RuntimeError(f"{name} must be a CUDA float tensor [B, C, h, w]")
+        if ref_fea.shape != tgt_fea.shape:
+            raise RuntimeError("ref_fea and tgt_fea must have the same shape")
+        B, Cc, h, w = ref_fea.shape
+        ref_fea, tgt_fea = ref_fea.contiguous(), tgt_fea.contiguous()
+        f32 = dict(device=self.device, dtype=torch.float32)
+        pose = pose.to(**f32).contiguous()
+        K = intrinsics4.to(**f32).contiguous()
+        Ki = intrinsics_inv4.to(**f32).contiguous()
+        if pose.numel() != B * 12 or K.numel() != B * 9 or Ki.numel() != B * 9:
+            raise RuntimeError("pose must be [B,3,4] and the intrinsics [B,3,3]")
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty(B, 2 * Cc, int(nlabel), h, w, **f32)
+            elif out.shape != (B, 2 * Cc, int(nlabel), h, w) or out.dtype != torch.float32 or not out.is_contiguous():
+                raise RuntimeError("out must be a contiguous float tensor [B, 2C, nlabel, h, w]")
+            rc = self.L.tv5_plane_sweep(self.ctx, self._stream(), ref_fea.data_ptr(), tgt_fea.data_ptr(),
+                                        pose.data_ptr(), K.data_ptr(), Ki.data_ptr(), B, Cc, h, w, int(nlabel),
+                                        float(mindepth), int(bool(by_depth)), out.data_ptr())
+        _check(self.ctx, rc, "tv5_plane_sweep")
+        return out
+
     # -- decomposition and refinement (polish_E.cu in the reference) ---------------------------
     def decompose_batch(self, E, want_angles=True, want_uv=True):
         """E: [B,3,3] (or [3,3]) float64 CUDA -> dict(angles [B,5], U [B,3,3], V [B,3,3])."""

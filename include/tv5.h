@@ -236,6 +236,26 @@ int tv5_pose_from_flow(tv5_ctx* ctx, void* stream, const float* flow, int B, int
                        int with_cheirality, float* E32_out, float* P32_out, tv5_result* result,
                        double* E_out, double* P_out);
 
+/*
+ * tv5_plane_sweep — plane-sweep cost volume from the estimated pose in one launch; replaces the
+ * label loop of PSNet.forward (models/PSNet.py:141-157) over inverse_warp
+ * (models/inverse_warp.py:121-153), the direct consumer of P.
+ *   ref_feat, tgt_feat  device [B,C,h,w] float32 (quarter-resolution features, C = 32)
+ *   pose                device [B,3,4] float32 [R|t] "from ref to target" (P32_out of
+ *                       tv5_pose_from_flow / the P_mat of pose_by_ransac)
+ *   K, Kinv             device [B,3,3] float32 intrinsics at FEATURE resolution
+ *                       (PSNet.py:130-133: K[:2,:] / 4, Kinv[:2,:2] * 4)
+ *   nlabel, mindepth    depth of plane i = mindepth*nlabel/(i+1), or (i+1)*mindepth if by_depth
+ *                       (cfg.PREDICT_BY_DEPTH)
+ *   cost                device [B,2C,nlabel,h,w] float32: channels [0,C) = ref_feat on every plane,
+ *                       [C,2C) = tgt_feat sampled bilinearly (zeros outside, align_corners=True)
+ * float32 like the reference; agreement with torch's own kernels is to float32 rounding of the
+ * sample position (tests state the bound).
+ */
+int tv5_plane_sweep(tv5_ctx* ctx, void* stream, const float* ref_feat, const float* tgt_feat,
+                    const float* pose, const float* K, const float* Kinv, int B, int C, int h, int w,
+                    int nlabel, float mindepth, int by_depth, float* cost);
+
 /* Testing/diagnostic switch: on != 0 makes the pose entry points score every hypothesis with the
  * float64 scorer (no float32 guard-band pass).  Results are identical by construction; the
  * tests use this to prove it. */

@@ -296,3 +296,71 @@ def _fma32(a, b, c):
     it with a float32 needs < 2*53 bits only in far-apart-exponent cases that the final rounding
     to float32 absorbs (double rounding can differ in 1 ulp; the tests allow it)."""
     return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# plane-sweep cost volume (consumer of P), numpy float32
+# ---------------------------------------------------------------------------------------------
+def plane_sweep_cost_volume(ref_fea, tgt_fea, pose, K, Kinv, nlabel, mindepth, by_depth=False,
+                            cuda_division=True):
+    """One batch element.  ref_fea, tgt_fea [C,h,w] float32; pose [3,4], K, Kinv [3,3] float32
+    (quarter-resolution intrinsics) -> cost [2C, nlabel, h, w] float32.
+
+    Restates PSNet.forward's label loop (models/PSNet.py:141-157): plane i has depth
+    mindepth*nlabel/(i+1) (or (i+1)*mindepth), the target features are inverse-warped onto it
+    (models/inverse_warp.py:121-153: cam = (Kinv pix) * depth :31-45; proj = K [R|t]; X/Z
+    normalised to [-1,1], out-of-range -> 2 :48-78; bilinear grid_sample, zero padding,
+    align_corners=True) and stacked under the reference features.  float32 throughout, 3-term
+    products accumulated k = 0,1,2 with fma like an SGEMM inner loop."""
+    f32 = np.float32
+    ref_fea = np.asarray(ref_fea, f32); tgt_fea = np.asarray(tgt_fea, f32)
+    pose = np.asarray(pose, f32); K = np.asarray(K, f32); Kinv = np.asarray(Kinv, f32)
+    C, h, w = ref_fea.shape
+    gx = np.broadcast_to(np.arange(w, dtype=f32)[None, :], (h, w))
+    gy = np.broadcast_to(np.arange(h, dtype=f32)[:, None], (h, w))
+    one = np.ones((h, w), f32)
+
+    def mat3(M, v):   # rows of M times the 3-vector field v, sgemm order
+        return [_fma32(M[r, 2], v[2], _fma32(M[r, 1], v[1], (M[r, 0] * v[0]).astype(f32))) for r in range(3)]
+
+    ray = mat3(Kinv, [gx, gy, one])
+    proj = np.empty((3, 4), f32)
+    for r in range(3):
+        for c in range(4):
+            proj[r, c] = _fma32(K[r, 2], pose[2, c], _fma32(K[r, 1], pose[1, c], f32(K[r, 0] * pose[0, c])))
+    cost = np.zeros((2 * C, nlabel, h, w), f32)
+    d2d = f32(f32(f32(1.0) * f32(mindepth)) * f32(nlabel))
+    for i in range(nlabel):
+        if by_depth:
+            depth = f32(f32(f32(1.0) * f32(i + 1)) * f32(mindepth))
+        elif cuda_division:
+            depth = f32(d2d * f32(f32(1.0) / f32(i + 1 + 1e-16)))
+        else:
+            depth = f32(d2d / f32(i + 1 + 1e-16))
+        cam = [(r * depth).astype(f32) for r in ray]
+        pc = [(v + proj[r, 3]).astype(f32) for r, v in enumerate(mat3(proj[:, :3], cam))]
+        Z = np.maximum(pc[2], f32(1e-3))
+        if cuda_division:
+            xn = ((f32(2.0) * (pc[0] / Z)).astype(f32) * f32(f32(1.0) / f32(w - 1))).astype(f32) - f32(1.0)
+            yn = ((f32(2.0) * (pc[1] / Z)).astype(f32) * f32(f32(1.0) / f32(h - 1))).astype(f32) - f32(1.0)
+        else:
+            xn = (f32(2.0) * (pc[0] / Z)).astype(f32) / f32(w - 1) - f32(1.0)
+            yn = (f32(2.0) * (pc[1] / Z)).astype(f32) / f32(h - 1) - f32(1.0)
+        xn = np.where((xn > 1) | (xn < -1), f32(2.0), xn).astype(f32)
+        yn = np.where((yn > 1) | (yn < -1), f32(2.0), yn).astype(f32)
+        ix = (((xn + f32(1.0)) / f32(2.0)) * f32(w - 1)).astype(f32)
+        iy = (((yn + f32(1.0)) / f32(2.0)) * f32(h - 1)).astype(f32)
+        x0, y0 = np.floor(ix), np.floor(iy)
+        wx1, wx0, wy1, wy0 = ix - x0, (x0 + f32(1.0)) - ix, iy - y0, (y0 + f32(1.0)) - iy
+        acc = np.zeros((C, h, w), f32)
+        for dx, dy, wt in ((0, 0, wx0 * wy0), (1, 0, wx1 * wy0), (0, 1, wx0 * wy1), (1, 1, wx1 * wy1)):
+            with np.errstate(invalid="ignore"):
+                xs = np.nan_to_num(x0, nan=-10.0).astype(np.int64) + dx
+                ys = np.nan_to_num(y0, nan=-10.0).astype(np.int64) + dy
+            ok = (xs >= 0) & (xs < w) & (ys >= 0) & (ys < h)
+            xc, yc = np.clip(xs, 0, w - 1), np.clip(ys, 0, h - 1)
+            term = _fma32(tgt_fea[:, yc, xc], wt[None].astype(f32), acc)
+            acc = np.where(ok[None], term, acc)
+        cost[:C, i] = ref_fea
+        cost[C:, i] = acc
+    return cost

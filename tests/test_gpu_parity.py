@@ -544,3 +544,52 @@ def test_pose_from_flow_equals_pose_on_reference_points(engine):
         oa, oc = oracle.flow_to_points(flow[b], Kinv[b], 10, pts[off[b]:off[b + 1]])
         one = engine.compute_pose(dev(oa), dev(oc), 2, THR)
         assert one.count == r.count[b] and torch.equal(one.E, r.E[b])
+
+
+# ---------------------------------------------------------------------------------------------
+# plane-sweep cost volume (consumer of P, models/PSNet.py:141-157)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("by_depth", [False, True])
+def test_plane_sweep_matches_oracle_and_reference_torch_loop(engine, by_depth):
+    import ref_planesweep_torch as rp
+    from test_oracle import sweep_case, sweep_tolerance
+    B, C, h, w, L = 2, 4, 24, 40, 8
+    ref, tgt, pose, K4, Kinv4 = sweep_case(B, C, h, w)
+    dv = [dev(a, torch.float32) for a in (ref, tgt, pose, K4, Kinv4)]
+    cost = engine.plane_sweep(*dv, L, 1.0, by_depth)
+    assert cost.shape == (B, 2 * C, L, h, w) and cost.dtype == torch.float32
+    mine = cost.cpu().numpy()
+    tol = sweep_tolerance(h, w, tgt)
+    ct = rp.cost_volume(*dv, L, 1.0, by_depth).cpu().numpy()      # the reference's torch ops on this GPU
+    for b in range(B):
+        co = oracle.plane_sweep_cost_volume(ref[b], tgt[b], pose[b], K4[b], Kinv4[b], L, 1.0, by_depth)
+        assert (mine[b, :C] == co[:C]).all() and (mine[b, :C] == ct[b, :C]).all()   # copies: exact
+        assert np.abs(mine[b, C:] - co[C:]).max() <= tol
+        assert np.abs(mine[b, C:] - ct[b, C:]).max() <= tol
+        # same operation sequence as the oracle: all but a handful of samples are bit-identical
+        assert (mine[b, C:] == co[C:]).mean() > 0.99
+
+
+def test_plane_sweep_full_size_properties(engine):
+    """PSNet's real shape (32 channels, 128 planes, quarter-resolution KITTI): identity pose at
+    any depth reproduces the target features; a NaN pose produces zeros, not a fault."""
+    import ref_planesweep_torch as rp
+    B, C, h, w, L = 1, 32, 92, 306, 128
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ref = torch.randn(B, C, h, w, device="cuda", generator=g)
+    tgt = torch.randn(B, C, h, w, device="cuda", generator=g)
+    K = synth.KITTI_K.copy(); K[:2] /= 4.0
+    K4 = dev(K[None], torch.float32); Kinv4 = dev(np.linalg.inv(K)[None], torch.float32)
+    eye = dev(np.concatenate([np.eye(3), np.zeros((3, 1))], 1)[None], torch.float32)
+    cost = engine.plane_sweep(ref, tgt, eye, K4, Kinv4, L, 1.0)
+    assert torch.equal(cost[:, :C], ref[:, :, None].expand(B, C, L, h, w))
+    # identity warp: sample positions are the pixel centres up to float32 rounding
+    assert (cost[:, C:] - tgt[:, :, None]).abs().max() < 8 * 1.2e-7 * w * 2 * float(tgt.abs().max())
+    # one plane against the reference's torch ops at full size
+    sc = synth.make_pair(10, seed=1)
+    pose = dev(np.concatenate([sc["R"], sc["t"][:, None]], 1)[None], torch.float32)
+    cost = engine.plane_sweep(ref, tgt, pose, K4, Kinv4, L, 1.0)
+    ct = rp.cost_volume(ref, tgt, pose, K4, Kinv4, L, 1.0)
+    assert (cost - ct).abs().max() < 8 * 1.2e-7 * w * 2 * float(tgt.abs().max())
+    bad = engine.plane_sweep(ref, tgt, pose * float("nan"), K4, Kinv4, 4, 1.0)
+    assert torch.equal(bad[:, C:], torch.zeros_like(bad[:, C:]))

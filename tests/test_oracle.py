@@ -247,3 +247,44 @@ def test_flow_scene_recovers_pose_through_oracle():
     r = oracle.ransac(x1, x2, sets, 1, 1e-4)
     assert synth.rotation_error_deg(r["P"][:, :3], sc["R"]) < 0.05
     assert r["count"] > 0.6 * x1.shape[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# plane-sweep cost volume: numpy oracle against the reference's torch loop (CPU tensors)
+# ---------------------------------------------------------------------------------------------
+def sweep_case(B=2, C=4, h=24, w=40, seed=0):
+    rng = np.random.default_rng(seed)
+    ref = rng.normal(0, 1, (B, C, h, w)).astype(np.float32)
+    tgt = rng.normal(0, 1, (B, C, h, w)).astype(np.float32)
+    K = synth.KITTI_K.copy()
+    K[:2] /= (synth.KITTI_HW[1] / w)
+    K4 = np.stack([K] * B).astype(np.float32)
+    Kinv4 = np.stack([np.linalg.inv(K)] * B).astype(np.float32)
+    R = synth.rodrigues((0.002, 0.01, -0.001))
+    t = np.array([0.03, -0.01, -0.8])
+    t /= np.linalg.norm(t)
+    pose = np.stack([np.concatenate([R, t[:, None]], 1)] * B).astype(np.float32)
+    pose[1:, :, 3] *= -0.5
+    return ref, tgt, pose, K4, Kinv4
+
+
+def sweep_tolerance(h, w, feat):
+    # the sample position carries a few float32 roundings (~8 ulp of a coordinate <= max(h,w));
+    # bilinear interpolation scales them by the local feature difference (<= 2 max|feat|)
+    return 8 * np.finfo(np.float32).eps * max(h, w) * 2 * float(np.abs(feat).max())
+
+
+@pytest.mark.parametrize("by_depth", [False, True])
+def test_plane_sweep_oracle_equals_reference_torch_loop(by_depth):
+    import torch
+    import ref_planesweep_torch as rp
+    B, C, h, w, L = 2, 4, 24, 40, 8
+    ref, tgt, pose, K4, Kinv4 = sweep_case(B, C, h, w)
+    ct = rp.cost_volume(*(torch.from_numpy(a) for a in (ref, tgt, pose, K4, Kinv4)), L, 1.0, by_depth).numpy()
+    assert ct.shape == (B, 2 * C, L, h, w)
+    for b in range(B):
+        co = oracle.plane_sweep_cost_volume(ref[b], tgt[b], pose[b], K4[b], Kinv4[b], L, 1.0, by_depth,
+                                            cuda_division=False)
+        assert (co[:C] == ct[b, :C]).all()                              # reference half: copies
+        assert np.abs(co[C:] - ct[b, C:]).max() <= sweep_tolerance(h, w, tgt)
+        assert (ct[b, C:] != 0).mean() > 0.2                            # the warp lands inside the image
