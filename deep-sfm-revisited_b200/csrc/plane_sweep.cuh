@@ -34,11 +34,22 @@ __device__ __forceinline__ float dot3_sgemm(float m0, float m1, float m2, float 
   return fmaf(m2, v2, fmaf(m1, v1, __fmul_rn(m0, v0)));
 }
 
-// grid (ceil(h*w / 256), L, B), block 256: thread = (pixel, plane)
+// grid (ceil((h*w + 31) / 256), L, B), block 256: thread = (pixel, plane).
+// The kernel is bound by L1 wavefronts, not instructions (ncu: l1tex 60 % at 49 % of HBM), so
+//  * the pixel index of a warp is shifted per plane so that its 128-byte stores into the volume
+//    are 128-byte aligned (one wavefront instead of two; h*w is odd for KITTI's 93 x 307), and
+//  * the east taps (x0+1) are taken from the next lane's west taps by shuffle whenever that lane
+//    samples the adjacent source pixel (almost always: disparity varies slowly along a row),
+//    which halves the gather wavefronts.
 __global__ void __launch_bounds__(256) plane_sweep(const SweepParams P) {
   const int hw = P.h * P.w;
-  const int p = blockIdx.x * 256 + threadIdx.x;
   const int i = blockIdx.y, b = blockIdx.z;
+  // element index of (b, channel, plane i, pixel 0) is i*hw modulo 32 for every channel (L*hw*c and
+  // b*2C*L*hw are multiples of 32 when L is; otherwise the shift is merely not optimal)
+  const int shift = (int)(((long long)i * hw) & 31);
+  const int p_raw = blockIdx.x * 256 + threadIdx.x - shift;
+  const bool live = p_raw >= 0 && p_raw < hw;
+  const int p = live ? p_raw : 0;
   __shared__ float s_proj[12], s_kinv[9];
   if (threadIdx.x < 12) {
     const int r = threadIdx.x >> 2, c = threadIdx.x & 3;
@@ -49,7 +60,6 @@ __global__ void __launch_bounds__(256) plane_sweep(const SweepParams P) {
     s_kinv[threadIdx.x - 32] = P.Kinv[9 * b + threadIdx.x - 32];
   }
   __syncthreads();
-  if (p >= hw) return;
   const int y = p / P.w, x = p - y * P.w;
   // depth of plane i  (PSNet.py:142,150-153)
   float depth;
@@ -86,28 +96,43 @@ __global__ void __launch_bounds__(256) plane_sweep(const SweepParams P) {
   const bool finite = (ix == ix) && (iy == iy) && fabsf(ix) < 1.0e9f && fabsf(iy) < 1.0e9f;
   const int x0 = finite ? (int)x0f : -10, y0 = finite ? (int)y0f : -10;
   const float wt[4] = {__fmul_rn(wx0, wy0), __fmul_rn(wx1, wy0), __fmul_rn(wx0, wy1), __fmul_rn(wx1, wy1)};
-  int off[4];
-  bool ok[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int xs = x0 + (k & 1), ys = y0 + (k >> 1);
-    ok[k] = xs >= 0 && xs < P.w && ys >= 0 && ys < P.h;
-    off[k] = ok[k] ? ys * P.w + xs : 0;
-  }
-  const float* __restrict__ tg = P.tgt + (size_t)b * P.C * hw;
+  // taps nw, ne, sw, se = base, base+1, base+w, base+w+1; pointers walk the channel planes so that
+  // the loop body carries no 64-bit index arithmetic (it was 55 % of the issued instructions)
+  const bool okx0 = x0 >= 0 && x0 < P.w, okx1 = x0 + 1 >= 0 && x0 + 1 < P.w;
+  const bool oky0 = y0 >= 0 && y0 < P.h, oky1 = y0 + 1 >= 0 && y0 + 1 < P.h;
+  const bool ok0 = okx0 && oky0, ok1 = okx1 && oky0, ok2 = okx0 && oky1, ok3 = okx1 && oky1;
+  const bool any = ok0 || ok1 || ok2 || ok3;
+  const ptrdiff_t base = any ? (ptrdiff_t)y0 * P.w + x0 : 0;   // only dereferenced under ok*
+  // does the next lane's west column coincide with this lane's east column?
+  const int lane = threadIdx.x & 31;
+  const int nx0 = __shfl_down_sync(0xffffffffu, x0, 1), ny0 = __shfl_down_sync(0xffffffffu, y0, 1);
+  const bool nlive = __shfl_down_sync(0xffffffffu, (int)live, 1) != 0;
+  const bool nbr = lane < 31 && nlive && nx0 == x0 + 1 && ny0 == y0;
+  const float* __restrict__ f0 = P.tgt + (size_t)b * P.C * hw + base;
+  const float* __restrict__ f1 = f0 + P.w;
   const float* __restrict__ rf = P.ref + (size_t)b * P.C * hw + p;
   const size_t plane = (size_t)P.L * hw;                       // stride between volume channels
-  float* __restrict__ out_ref = P.cost + ((size_t)b * 2 * P.C * P.L + i) * hw + p;
-  float* __restrict__ out_tgt = out_ref + (size_t)P.C * plane;
+  float* __restrict__ o_r = P.cost + ((size_t)b * 2 * P.C * P.L + i) * hw + p;
+  float* __restrict__ o_t = o_r + (size_t)P.C * plane;
 #pragma unroll 4
   for (int c = 0; c < P.C; ++c) {
-    const float* __restrict__ f = tg + (size_t)c * hw;
+    const float v00 = ok0 ? __ldg(f0) : 0.0f;
+    const float v10 = ok2 ? __ldg(f1) : 0.0f;
+    const float n00 = __shfl_down_sync(0xffffffffu, v00, 1);
+    const float n10 = __shfl_down_sync(0xffffffffu, v10, 1);
+    const float v01 = nbr ? n00 : ((ok1) ? __ldg(f0 + 1) : 0.0f);
+    const float v11 = nbr ? n10 : ((ok3) ? __ldg(f1 + 1) : 0.0f);
     float acc = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (ok[k]) acc = fmaf(__ldg(f + off[k]), wt[k], acc);
-    __stcs(out_tgt + (size_t)c * plane, acc);
-    __stcs(out_ref + (size_t)c * plane, __ldg(rf + (size_t)c * hw));
+    if (ok0) acc = fmaf(v00, wt[0], acc);
+    if (ok1) acc = fmaf(v01, wt[1], acc);
+    if (ok2) acc = fmaf(v10, wt[2], acc);
+    if (ok3) acc = fmaf(v11, wt[3], acc);
+    if (live) {
+      __stcs(o_t, acc);
+      __stcs(o_r, __ldg(rf));
+    }
+    f0 += hw; f1 += hw; rf += hw;
+    o_t += plane; o_r += plane;
   }
 }
 

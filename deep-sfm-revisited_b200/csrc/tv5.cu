@@ -1541,7 +1541,7 @@ int tv5_plane_sweep(tv5_ctx* ctx, void* stream, const float* ref_feat, const flo
   SweepParams P;
   P.ref = ref_feat; P.tgt = tgt_feat; P.pose = pose; P.K = K; P.Kinv = Kinv; P.cost = cost;
   P.C = C; P.h = h; P.w = w; P.L = nlabel; P.mindepth = mindepth; P.by_depth = by_depth ? 1 : 0;
-  plane_sweep<<<dim3((unsigned)((h * w + 255) / 256), nlabel, B), 256, 0, (cudaStream_t)stream>>>(P);
+  plane_sweep<<<dim3((unsigned)((h * w + 31 + 255) / 256), nlabel, B), 256, 0, (cudaStream_t)stream>>>(P);
   TV5_CUDA(ctx, cudaGetLastError());
   return TV5_OK;
 }

