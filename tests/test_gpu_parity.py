@@ -601,3 +601,37 @@ def test_plane_sweep_full_size_properties(engine):
     assert (diff > tol).float().mean() < 1e-3
     bad = engine.plane_sweep(ref, tgt, pose * float("nan"), K4, Kinv4, 4, 1.0)
     assert torch.equal(bad[:, C:], torch.zeros_like(bad[:, C:]))
+
+
+# ---------------------------------------------------------------------------------------------
+# chunked submissions: host-buffer entry point and the optional solver/scorer overlap
+# ---------------------------------------------------------------------------------------------
+def test_chunked_host_path_and_overlap_equal_plain_submission(engine):
+    """40 ragged pairs: (a) one plain device submission, (b) the host-buffer entry point (chunks of
+    pairs start as their copies land), (c) the two-stream overlap mode — identical results."""
+    rng = np.random.default_rng(3)
+    ns = [int(n) for n in rng.integers(300, 3000, 40)]
+    ns[7], ns[23] = 5, 2999
+    pairs = [synth.make_pair(n, **{**synth.pair_variation(i), "seed": 900 + i}) for i, n in enumerate(ns)]
+    x1h = np.concatenate([p["x1"] for p in pairs]); x2h = np.concatenate([p["x2"] for p in pairs])
+    off = np.r_[0, np.cumsum(ns)]
+    sets = np.stack([synth.make_sets(n, 512, 950 + i) for i, n in enumerate(ns)])
+    plain = engine.compute_pose_batch(dev(x1h), dev(x2h), off, 1, THR, sets=dev(sets, torch.int32))
+    Eh, Ph, sth = engine.compute_pose_batch_host(x1h, x2h, off, 1, THR, sets=sets)
+    assert (Eh == plain.E.cpu().numpy()).all() and (Ph == plain.P.cpu().numpy()).all()
+    assert (sth[:, :5] == plain.stats.cpu().numpy()[:, :5]).all()
+    try:
+        engine.set_overlap(True)
+        assert engine.pipeline_chunks(40) == 2
+        ov = engine.compute_pose_batch(dev(x1h), dev(x2h), off, 1, THR, sets=dev(sets, torch.int32), want_mask=True)
+        Eh2, Ph2, sth2 = engine.compute_pose_batch_host(x1h, x2h, off, 1, THR, sets=sets)
+    finally:
+        engine.set_overlap(False)
+    assert torch.equal(ov.E, plain.E) and torch.equal(ov.P, plain.P)
+    assert torch.equal(ov.stats[:, :5], plain.stats[:, :5])
+    assert (Eh2 == Eh).all() and (sth2[:, :5] == sth[:, :5]).all()
+    # the masks returned by the overlapped run are the winners' exact masks
+    for i in (0, 7, 23, 39):
+        a, b = off[i], off[i + 1]
+        c, m = oracle.score(x1h[a:b], x2h[a:b], ov.E[i].cpu().numpy().reshape(1, 9), THR, want_mask=True)
+        assert int(c[0]) == int(ov.count[i]) and (ov.mask[a:b].cpu().numpy() == m[0]).all()
