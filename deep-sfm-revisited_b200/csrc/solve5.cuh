@@ -489,12 +489,24 @@ struct FastChain {
 
 __device__ __forceinline__ int fast_changes(const FastChain& s, double x) {
   double f[11];
+  const double x2 = x * x;
 #pragma unroll
   for (int k = 0; k <= 10; ++k) {
-    double v = s.c[k][10 - k];
+    const int deg = 10 - k;
+    if (deg >= 5) {   // long members: even and odd parts as two independent chains in x^2
+      const int te = deg & ~1, to = (deg - 1) | 1;   // top even / odd exponent
+      double ve = s.c[k][te], vo = s.c[k][to];
 #pragma unroll
-    for (int i = 9 - k; i >= 0; --i) v = fma(v, x, s.c[k][i]);
-    f[k] = v;
+      for (int i = te - 2; i >= 0; i -= 2) ve = fma(ve, x2, s.c[k][i]);
+#pragma unroll
+      for (int i = to - 2; i >= 1; i -= 2) vo = fma(vo, x2, s.c[k][i]);
+      f[k] = fma(vo, x, ve);
+    } else {
+      double v = s.c[k][deg];
+#pragma unroll
+      for (int i = deg - 1; i >= 0; --i) v = fma(v, x, s.c[k][i]);
+      f[k] = v;
+    }
   }
   int ch = 0;
 #pragma unroll
@@ -556,6 +568,25 @@ __device__ __forceinline__ void eval_p_dp(const double (&p)[11], double x, doubl
   for (int i = 9; i >= 0; --i) { df = fma(df, x, f); f = fma(f, x, p[i]); }
 }
 
+// The same two values with short dependency chains (the solver is FP64-latency bound): p and its
+// derivative are split into even and odd parts, four independent Horner chains in x^2 of length
+// <= 5 instead of one chain of 20.  dq = chain member 1 = p' / 10 (fast_build).
+__device__ __forceinline__ void eval_p_dp_split(const double (&p)[11], const double (&dq)[11], double x,
+                                                double& f, double& df) {
+  const double x2 = x * x;
+  double fe = p[10], fo = p[9], de = dq[8], dd = dq[9];
+#pragma unroll
+  for (int i = 8; i >= 0; i -= 2) fe = fma(fe, x2, p[i]);
+#pragma unroll
+  for (int i = 7; i >= 1; i -= 2) fo = fma(fo, x2, p[i]);
+#pragma unroll
+  for (int i = 6; i >= 0; i -= 2) de = fma(de, x2, dq[i]);
+#pragma unroll
+  for (int i = 7; i >= 1; i -= 2) dd = fma(dd, x2, dq[i]);
+  f = fma(fo, x, fe);
+  df = 10.0 * fma(dd, x, de);
+}
+
 // one root isolated in [lo,hi] by the Sturm counts (vlo - vhi == 1)
 __device__ __forceinline__ double fast_refine(const FastChain& s, double lo, double hi, int vlo) {
   const double (&p)[11] = s.c[0];
@@ -581,7 +612,7 @@ __device__ __forceinline__ double fast_refine(const FastChain& s, double lo, dou
   // bracketed Newton (bisect when Newton leaves the bracket or converges too slowly)
   double xl = flo < 0.0 ? lo : hi, xh = flo < 0.0 ? hi : lo;
   double x = 0.5 * (lo + hi), dxold = fabs(hi - lo), dx = dxold, f, df;
-  eval_p_dp(p, x, f, df);
+  eval_p_dp_split(p, s.c[1], x, f, df);
   for (int it = 0; it < 64; ++it) {
 #ifdef TV5_SOLVE_COUNT
     atomicAdd(&g_solve_prof[10], 1ull);
@@ -590,7 +621,7 @@ __device__ __forceinline__ double fast_refine(const FastChain& s, double lo, dou
     dxold = dx;
     if (bisect) { dx = 0.5 * (xh - xl); x = xl + dx; } else { dx = f / df; x -= dx; }
     if (!(fabs(dx) > 1.0e-15 * fabs(x))) break;
-    eval_p_dp(p, x, f, df);
+    eval_p_dp_split(p, s.c[1], x, f, df);
     if (f == 0.0) break;
     if (f < 0.0) xl = x; else xh = x;
   }

@@ -182,11 +182,17 @@ __device__ __forceinline__ void hidden_matrix_from_rows(const double (*sR)[kCoop
 // pass valid = false and still take part in the cooperative phase).  Register pressure is kept
 // down for the root finder (66 chain coefficients in registers) by parking everything else in
 // shared memory meanwhile: sQ = the five point pairs, sB = basis, sR = reduced rows.
+// emit(j, E) is called for every solution kept (j = its index in the set's list) while E is still
+// in registers.
+struct NoEmit {
+  __device__ __forceinline__ void operator()(int, const double (&)[9]) const {}
+};
+template <typename Emit = NoEmit>
 __device__ inline int solve_minimal_set_coop(bool valid, const double (&q_in)[5][2],
                                              const double (&qp_in)[5][2], bool with_cheirality,
                                              double* E_out, double* P_out, int* n_roots_out,
                                              double (*sB)[kCoopStride], double (*sR)[kCoopStride], double (*sQ)[kCoopStride],
-                                             int* sOk) {
+                                             int* sOk, Emit emit = Emit()) {
   const int lane = threadIdx.x & 31;
   *n_roots_out = 0;
   bool ok = valid;
@@ -250,6 +256,7 @@ __device__ inline int solve_minimal_set_coop(bool valid, const double (&q_in)[5]
     }
 #pragma unroll
     for (int c = 0; c < 9; ++c) E_out[9 * nv + c] = E[c];
+    emit(nv, E);
     ++nv;
   }
   TV5_TICK(5);

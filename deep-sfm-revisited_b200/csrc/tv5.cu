@@ -223,23 +223,23 @@ __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ de
   double* E = E_list + s * 90;
   double* P = P_list ? P_list + s * 120 : nullptr;
   int nr = 0;
-  const int nv = solve_minimal_set_coop(valid, q, qp, with_cheirality != 0, E, P, &nr, sB, sR, sQ, sOk);
+  // float32 hypothesis records are built while E is in registers; one slot per solution
+  // (slot order is arbitrary: every record carries its id = set*16 + index)
+  auto emit = [&](int j, const double (&Ereg)[9]) {
+    if (!hyp) return;
+    const int slot = atomicAdd(&state[b].M, 1);
+    const size_t o = (size_t)b * H * 10 + slot;
+    Hyp32 r;
+    make_hyp32(Ereg, state[b].s_scale, r);
+    hyp[o] = r;
+    hyp_id[o] = h * 16 + j;
+    notin[o] = 0u;
+    out[o] = 0u;
+  };
+  const int nv = solve_minimal_set_coop(valid, q, qp, with_cheirality != 0, E, P, &nr, sB, sR, sQ, sOk, emit);
   if (!valid) return;
   n_valid[s] = nv;
   if (n_roots) n_roots[s] = nr;
-  if (hyp && nv > 0) {
-    const int base = atomicAdd(&state[b].M, nv);
-    const size_t o = (size_t)b * H * 10 + base;
-    const double sc = state[b].s_scale;
-    for (int j = 0; j < nv; ++j) {
-      Hyp32 r;
-      make_hyp32(E + 9 * j, sc, r);
-      hyp[o + j] = r;
-      hyp_id[o + j] = h * 16 + j;
-      notin[o + j] = 0u;
-      out[o + j] = 0u;
-    }
-  }
 }
 
 // float32 hypothesis records for an arbitrary E list (tv5_score_bounds)
