@@ -378,7 +378,7 @@ def run_ours(args):
     other = {}
     try:
         Hh, Ww = synth.KITTI_HW
-        Bf = 16                                   # 16 dense KITTI frames: 290 MB of traffic > L2
+        Bf = 64                                   # 64 dense KITTI frames: 1.1 GB of traffic >> L2
         flow = torch.randn(Bf, 2, Hh, Ww, device=dev) * 3.0
         Kinv = torch.from_numpy(np.linalg.inv(synth.KITTI_K).astype(np.float32)).to(dev).repeat(Bf, 1, 1)
         ms_f = timed(lambda: eng.flow_to_points(flow, Kinv, 10))
