@@ -344,6 +344,15 @@ def run_ours(args):
             "sampson_evals_per_s": evals / t_score, "kernel_ms": stage_ms["score_bounds"],
             "note": "34 FLOP per Sampson evaluation (SURVEY 8(d)); the kernel executes 34 FP32 lane-ops per evaluation (17 FFMA2 per two evaluations) "
                     "(guard band included), so its FP32-pipe utilisation is about frac"}
+    try:   # DRAM bytes of one launch of exactly this workload, from the committed ncu capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "score_bounds_traffic.json")))
+        if B == PAIRS_PER_GPU:
+            roof["traffic"] = tr["dram_bytes_per_launch"]
+            roof["traffic_source"] = tr["source"]
+            # what the kernel must read once: packed point pairs + hypothesis records + counters
+            roof["algorithmic_bytes_per_launch"] = float(B * ((N_CORR + 1) // 2) * 48 + M_total * (48 + 8))
+    except Exception:
+        pass
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         roof["hbm_gbs_measured_peak"] = peaks.get("hbm_gbs")
