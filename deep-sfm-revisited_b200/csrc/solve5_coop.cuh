@@ -187,12 +187,19 @@ __device__ __forceinline__ void hidden_matrix_from_rows(const double (*sR)[kCoop
 struct NoEmit {
   __device__ __forceinline__ void operator()(int, const double (&)[9]) const {}
 };
-template <typename Emit = NoEmit>
+// reload(q, qp) (optional) re-gathers the five point pairs for the pose phase; without it they
+// are parked in sQ during the root phase.  Re-gathering saves 5 KB of shared memory per warp
+// (8 instead of 7 resident warps per SM).
+struct NoReload {
+  static constexpr bool kEnabled = false;
+  __device__ __forceinline__ void operator()(double (&)[5][2], double (&)[5][2]) const {}
+};
+template <typename Emit = NoEmit, typename Reload = NoReload>
 __device__ inline int solve_minimal_set_coop(bool valid, const double (&q_in)[5][2],
                                              const double (&qp_in)[5][2], bool with_cheirality,
                                              double* E_out, double* P_out, int* n_roots_out,
                                              double (*sB)[kCoopStride], double (*sR)[kCoopStride], double (*sQ)[kCoopStride],
-                                             int* sOk, Emit emit = Emit()) {
+                                             int* sOk, Emit emit = Emit(), Reload reload = Reload()) {
   const int lane = threadIdx.x & 31;
   *n_roots_out = 0;
   bool ok = valid;
@@ -208,10 +215,12 @@ __device__ inline int solve_minimal_set_coop(bool valid, const double (&q_in)[5]
     for (int k = 0; k < 4; ++k)
 #pragma unroll
       for (int c = 0; c < 9; ++c) sB[k * 9 + c][lane] = ok ? B[k][c] : (k == 3 ? 1.0 : 0.0);
+    if (!Reload::kEnabled) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      sQ[4 * i][lane] = q_in[i][0]; sQ[4 * i + 1][lane] = q_in[i][1];
-      sQ[4 * i + 2][lane] = qp_in[i][0]; sQ[4 * i + 3][lane] = qp_in[i][1];
+      for (int i = 0; i < 5; ++i) {
+        sQ[4 * i][lane] = q_in[i][0]; sQ[4 * i + 1][lane] = q_in[i][1];
+        sQ[4 * i + 2][lane] = qp_in[i][0]; sQ[4 * i + 3][lane] = qp_in[i][1];
+      }
     }
   }
   __syncwarp();
@@ -239,10 +248,14 @@ __device__ inline int solve_minimal_set_coop(bool valid, const double (&q_in)[5]
   for (int k = 0; k < 4; ++k)
 #pragma unroll
     for (int c = 0; c < 9; ++c) B[k][c] = sB[k * 9 + c][lane];
+  if (Reload::kEnabled) {
+    reload(q, qp);
+  } else {
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    q[i][0] = sQ[4 * i][lane]; q[i][1] = sQ[4 * i + 1][lane];
-    qp[i][0] = sQ[4 * i + 2][lane]; qp[i][1] = sQ[4 * i + 3][lane];
+    for (int i = 0; i < 5; ++i) {
+      q[i][0] = sQ[4 * i][lane]; q[i][1] = sQ[4 * i + 1][lane];
+      qp[i][0] = sQ[4 * i + 2][lane]; qp[i][1] = sQ[4 * i + 3][lane];
+    }
   }
   int nv = 0;
   for (int i = 0; i < nr; ++i) {

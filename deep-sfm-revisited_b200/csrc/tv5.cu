@@ -189,6 +189,24 @@ __device__ __forceinline__ void make_hyp32(const double* E, double sc, Hyp32& h)
   h.pad = 0.f;
 }
 
+// re-gathers the five point pairs of minimal set h (solve5_coop.cuh: Reload)
+struct GatherSet {
+  static constexpr bool kEnabled = true;
+  const PairDesc& d;
+  int h;
+  __device__ __forceinline__ void operator()(double (&q)[5][2], double (&qp)[5][2]) const {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      int idx = d.sets[5 * (size_t)h + i];
+      idx = max(0, min(idx, d.n - 1));
+      const double2 a = reinterpret_cast<const double2*>(d.x1)[idx];
+      const double2 c = reinterpret_cast<const double2*>(d.x2)[idx];
+      q[i][0] = a.x; q[i][1] = a.y;
+      qp[i][0] = c.x; qp[i][1] = c.y;
+    }
+  }
+};
+
 __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ desc,
                                                  PairState* __restrict__ state, int H,
                                                  int with_cheirality,
@@ -202,23 +220,15 @@ __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ de
                                                  uint32_t* __restrict__ out) {
   __shared__ double sB[kCoopBasisDoubles][kCoopStride];
   __shared__ double sR[kCoopRowsDoubles][kCoopStride];
-  __shared__ double sQ[kCoopPointDoubles][kCoopStride];
   __shared__ int sOk[32];
   const int h_raw = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = h_raw < H;        // every lane takes part in the cooperative phase
   const int h = valid ? h_raw : H - 1;
   const int b = blockIdx.y;
   const PairDesc d = desc[b];
+  const GatherSet gather{d, h};
   double q[5][2], qp[5][2];
-#pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    int idx = d.sets[5 * (size_t)h + i];
-    idx = max(0, min(idx, d.n - 1));
-    const double2 a = reinterpret_cast<const double2*>(d.x1)[idx];
-    const double2 c = reinterpret_cast<const double2*>(d.x2)[idx];
-    q[i][0] = a.x; q[i][1] = a.y;
-    qp[i][0] = c.x; qp[i][1] = c.y;
-  }
+  gather(q, qp);
   const size_t s = (size_t)b * H + h;
   double* E = E_list + s * 90;
   double* P = P_list ? P_list + s * 120 : nullptr;
@@ -236,7 +246,7 @@ __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ de
     notin[o] = 0u;
     out[o] = 0u;
   };
-  const int nv = solve_minimal_set_coop(valid, q, qp, with_cheirality != 0, E, P, &nr, sB, sR, sQ, sOk, emit);
+  const int nv = solve_minimal_set_coop(valid, q, qp, with_cheirality != 0, E, P, &nr, sB, sR, nullptr, sOk, emit, gather);
   if (!valid) return;
   n_valid[s] = nv;
   if (n_roots) n_roots[s] = nr;
