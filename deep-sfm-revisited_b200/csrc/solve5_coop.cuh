@@ -17,7 +17,10 @@ namespace tv5 {
 constexpr int kCoopBasisDoubles = 36;
 constexpr int kCoopRowsDoubles = 60;
 constexpr int kCoopJam = 1;      // rounds carried through the elimination together (2 measured slower: spills)
-constexpr int kCoopStride = 33;  // padded lane stride: conflict-free for fixed-set/varying-element access too
+#ifndef TV5_COOP_STRIDE
+#define TV5_COOP_STRIDE 33
+#endif
+constexpr int kCoopStride = TV5_COOP_STRIDE;  // padded lane stride: conflict-free for fixed-set/varying-element access too
 constexpr int kCoopPointDoubles = 20;
 
 // sB[e][lane]: basis coefficient e = k*9 + c of the lane's set (k: unknown w,x,y,1; c = 3i+j)
