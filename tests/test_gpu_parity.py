@@ -635,3 +635,71 @@ def test_chunked_host_path_and_overlap_equal_plain_submission(engine):
         a, b = off[i], off[i + 1]
         c, m = oracle.score(x1h[a:b], x2h[a:b], ov.E[i].cpu().numpy().reshape(1, 9), THR, want_mask=True)
         assert int(c[0]) == int(ov.count[i]) and (ov.mask[a:b].cpu().numpy() == m[0]).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# C ABI error behaviour: codes, never exit(), never print (essential_matrix.cu:17-24 calls exit)
+# ---------------------------------------------------------------------------------------------
+def test_cabi_rejects_bad_arguments_with_error_codes(engine):
+    import ctypes as C
+    L, ctx = engine.L, engine.ctx
+    x = dev(np.random.default_rng(0).normal(size=(64, 2)))
+    E = torch.empty(9, dtype=torch.float64, device="cuda")
+    P = torch.empty(12, dtype=torch.float64, device="cuda")
+    res = torch.zeros(8, dtype=torch.int32, device="cuda")
+    ok = (ctx, None, x.data_ptr(), x.data_ptr(), 64, None, 1, 64, 64, 1e-3, 1, E.data_ptr(), P.data_ptr(), res.data_ptr(), None)
+
+    def call(**kw):
+        a = list(ok)
+        for k, v in kw.items():
+            a[int(k[1:])] = v
+        return L.tv5_compute_pose(*a)
+
+    assert call() == 0
+    assert call(_0=None) == -1                      # no context
+    assert call(_2=None) == -1                      # x1 null
+    assert call(_4=0) == -1 and call(_4=-5) == -1   # N < 1
+    assert call(_6=0) == -1                         # iters < 1
+    assert call(_9=0.0) == -1 and call(_9=float("nan")) == -1 and call(_9=-1.0) == -1   # threshold
+    assert call(_11=None) == -1 and call(_13=None) == -1                                 # outputs
+    assert L.tv5_strerror(-1) == b"invalid argument" and L.tv5_strerror(-2) == b"CUDA runtime error"
+    assert L.tv5_score(ctx, None, x.data_ptr(), x.data_ptr(), 64, None, 3, 1e-3, res.data_ptr(), None) == -1
+    assert L.tv5_plane_sweep(ctx, None, None, None, None, None, None, 1, 1, 4, 4, 1, C.c_float(1.0), 0, None) == -1
+    assert L.tv5_flow_to_points(ctx, None, x.data_ptr(), 1, 8, 8, x.data_ptr(), 0, 4, None, None, E.data_ptr(), E.data_ptr()) == -1  # margin eats the image
+    assert L.tv5_optimise(ctx, None, x.data_ptr(), x.data_ptr(), -1, None, E.data_ptr(), 1e-4, 1.0, 3, None) == -1
+    torch.cuda.synchronize()                        # the context is still healthy
+    assert call() == 0
+
+
+def test_fewer_than_five_points_and_degenerate_sets(engine):
+    """N < 5 forces repeated indices in every minimal set (the reference's RNG does the same):
+    the solver reports no solution instead of faulting, the pose call returns the zero result."""
+    x1 = dev(np.array([[0.1, 0.2], [0.3, -0.1], [-0.2, 0.05]]))
+    x2 = dev(np.array([[0.11, 0.2], [0.31, -0.12], [-0.19, 0.04]]))
+    r = engine.compute_pose(x1, x2, 1, THR)
+    assert r.count >= 0 and torch.isfinite(r.E).all() and torch.isfinite(r.P).all()
+    sets = np.zeros((512, 5), np.int32)             # every set = the same point five times
+    r = engine.compute_pose(x1, x2, 1, THR, sets=dev(sets, torch.int32))
+    assert r.count == 0 and r.best_set == -1 and float(r.E.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_scoring_random_property_counts_equal_oracle(engine, seed):
+    """Random (not geometrically meaningful) E, points and thresholds, ragged sizes: exact counts,
+    guard-band brackets and masks against the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(1, 3000))
+    M = int(rng.integers(1, 300))
+    x1 = rng.normal(0, rng.uniform(0.05, 2.0), (n, 2))
+    x2 = x1 + rng.normal(0, 10.0 ** rng.uniform(-5, -1), (n, 2))
+    E = rng.normal(0, 1, (M, 9)) * 10.0 ** rng.uniform(-3, 3, (M, 1))
+    thr = 10.0 ** rng.uniform(-5, -1)
+    c_or, m_or = oracle.score(x1, x2, E, thr, want_mask=True)
+    cnt, masks = engine.score(dev(x1), dev(x2), dev(E), thr, want_mask=True)
+    assert (cnt.cpu().numpy() == c_or).all() and (unpack_masks(masks, n) == m_or).all()
+    try:
+        lo, hi = engine.score_bounds(dev(x1), dev(x2), dev(E), thr)
+    except Exception:
+        return                                      # band too wide for float32: the pipeline uses float64
+    lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
+    assert (lo <= c_or).all() and (c_or <= hi).all()
