@@ -587,14 +587,38 @@ __device__ __forceinline__ void eval_p_dp_split(const double (&p)[11], const dou
   df = 10.0 * fma(dd, x, de);
 }
 
-// one root isolated in [lo,hi] by the Sturm counts (vlo - vhi == 1)
-__device__ __forceinline__ double fast_refine(const FastChain& s, double lo, double hi, int vlo) {
+// Newton part of the refinement: p has opposite signs at lo and hi (flo = p(lo)).  dq = p'/10.
+__device__ __forceinline__ double newton_bracketed(const double (&p)[11], const double (&dq)[11], double lo,
+                                                   double hi, double flo) {
+  // bracketed Newton (bisect when Newton leaves the bracket or converges too slowly)
+  double xl = flo < 0.0 ? lo : hi, xh = flo < 0.0 ? hi : lo;
+  double x = 0.5 * (lo + hi), dxold = fabs(hi - lo), dx = dxold, f, df;
+  eval_p_dp_split(p, dq, x, f, df);
+  for (int it = 0; it < 64; ++it) {
+#ifdef TV5_SOLVE_COUNT
+    atomicAdd(&g_solve_prof[10], 1ull);
+#endif
+    const bool bisect = (((x - xh) * df - f) * ((x - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df));
+    dxold = dx;
+    if (bisect) { dx = 0.5 * (xh - xl); x = xl + dx; } else { dx = f / df; x -= dx; }
+    if (!(fabs(dx) > 1.0e-15 * fabs(x))) break;
+    eval_p_dp_split(p, dq, x, f, df);
+    if (f == 0.0) break;
+    if (f < 0.0) xl = x; else xh = x;
+  }
+  return x;
+}
+
+// One root isolated in [lo,hi] by the Sturm counts (vlo - vhi == 1): make the bracket one with a
+// sign change of p.  Returns 0 = bracket ready (flo = p(lo)), 1 = root found exactly / bracket
+// collapsed (lo = the answer).
+__device__ __forceinline__ int prepare_bracket(const FastChain& s, double& lo, double& hi, int vlo, double& flo) {
   const double (&p)[11] = s.c[0];
-  double flo, fhi, d;
+  double fhi, d;
   eval_p_dp(p, lo, flo, d);
   eval_p_dp(p, hi, fhi, d);
-  if (flo == 0.0) return lo;
-  if (fhi == 0.0) return hi;
+  if (flo == 0.0) return 1;
+  if (fhi == 0.0) { lo = hi; return 1; }
   if ((flo < 0.0) == (fhi < 0.0)) {  // rare: no sign change at the ends; shrink with Sturm counts
     for (int it = 0; it < 60; ++it) {
       const double mid = 0.5 * (lo + hi);
@@ -604,38 +628,32 @@ __device__ __forceinline__ double fast_refine(const FastChain& s, double lo, dou
       if (vlo - fast_changes(s, mid) == 0) { lo = mid; flo = fm; } else { hi = mid; fhi = fm; }
       if ((flo < 0.0) != (fhi < 0.0)) break;
     }
-    if ((flo < 0.0) == (fhi < 0.0)) return 0.5 * (lo + hi);
+    if ((flo < 0.0) == (fhi < 0.0)) { lo = 0.5 * (lo + hi); return 1; }
   }
+  return 0;
+}
+
+__device__ __forceinline__ double fast_refine(const FastChain& s, double lo, double hi, int vlo) {
+  double flo;
+  if (prepare_bracket(s, lo, hi, vlo, flo)) return lo;
 #ifdef TV5_SOLVE_COUNT
   atomicAdd(&g_solve_prof[11], 1ull);
 #endif
-  // bracketed Newton (bisect when Newton leaves the bracket or converges too slowly)
-  double xl = flo < 0.0 ? lo : hi, xh = flo < 0.0 ? hi : lo;
-  double x = 0.5 * (lo + hi), dxold = fabs(hi - lo), dx = dxold, f, df;
-  eval_p_dp_split(p, s.c[1], x, f, df);
-  for (int it = 0; it < 64; ++it) {
-#ifdef TV5_SOLVE_COUNT
-    atomicAdd(&g_solve_prof[10], 1ull);
-#endif
-    const bool bisect = (((x - xh) * df - f) * ((x - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df));
-    dxold = dx;
-    if (bisect) { dx = 0.5 * (xh - xl); x = xl + dx; } else { dx = f / df; x -= dx; }
-    if (!(fabs(dx) > 1.0e-15 * fabs(x))) break;
-    eval_p_dp_split(p, s.c[1], x, f, df);
-    if (f == 0.0) break;
-    if (f < 0.0) xl = x; else xh = x;
-  }
-  return x;
+  return newton_bracketed(s.c[0], s.c[1], lo, hi, flo);
 }
 
-// roots ascending; returns the count.  poly[0..10] ascending powers of w.
-__device__ inline int real_roots_deg10(const double (&poly)[11], double (&roots)[10]) {
+// Isolation of the real roots of poly (ascending powers of w) in the scaled variable u = w * fac.
+// Returns the number of intervals ni (ascending); interval i holds exactly one root of the monic
+// scaled polynomial s.c[0] in [ilo, ihi] with Sturm count ivlo at ilo, or is a collapsed cluster
+// (ivlo < 0, root := ilo).  Returns -1 when the generic (local-memory) path must be used.
+__device__ inline int isolate_roots_deg10(const double (&poly)[11], FastChain& s, double& back,
+                                          double (&ilo)[10], double (&ihi)[10], int (&ivlo)[10]) {
+  back = 1.0;
   const double lead = poly[10];
   if (lead == 0.0) return 0;
 #ifdef TV5_SOLVE_PROFILE
   long long rt_prev = clock64();
 #endif
-  FastChain s;
   const double inv = 1.0 / lead;
   bool finite = true;
 #pragma unroll
@@ -653,7 +671,8 @@ __device__ inline int real_roots_deg10(const double (&poly)[11], double (&roots)
 #pragma unroll
     for (int i = 9; i >= 0; --i) { s.c[0][i] *= mult; mult *= fac; }
   }
-  if (!fast_build(s)) return real_roots_deg10_generic(poly, roots);
+  back = 1.0 / fac;
+  if (!fast_build(s)) return -1;
   TV5_RTICK(6);
   if (fast_changes_inf(s, true) - fast_changes_inf(s, false) <= 0) return 0;
   double bound = 0.0;
@@ -664,11 +683,10 @@ __device__ inline int real_roots_deg10(const double (&poly)[11], double (&roots)
   if (vlo0 - vhi0 <= 0) return 0;
 
   // flat isolation loop: every trip performs exactly one Sturm count
-  double slo[12], shi[12], ilo[10], ihi[10];
-  int svlo[12], svhi[12], ivlo[10];
+  double slo[12], shi[12];
+  int svlo[12], svhi[12];
   int sp = 1, ni = 0;
   slo[0] = -bound; shi[0] = bound; svlo[0] = vlo0; svhi[0] = vhi0;
-  int nr = 0;
   for (int trip = 0; trip < 400 && sp > 0; ++trip) {
 #ifdef TV5_SOLVE_COUNT
     atomicAdd(&g_solve_prof[8], 1ull);
@@ -694,10 +712,8 @@ __device__ inline int real_roots_deg10(const double (&poly)[11], double (&roots)
     const int vmid = fast_changes(s, mid);
     const int n1 = svlo[t] - vmid, n2 = vmid - svhi[t];
     if (n1 > 0 && n2 > 0 && sp < 12) {   // split: right half below, left half on top (popped first)
-      const int vhi = svhi[t];
       slo[t] = mid; svlo[t] = vmid;                       // right: [mid, hi]
       slo[sp] = lo; shi[sp] = mid; svlo[sp] = n1 + vmid; svhi[sp] = vmid; ++sp;
-      (void)vhi;
     } else if (n1 == 0) {
       slo[t] = mid; svlo[t] = vmid;
     } else {
@@ -705,11 +721,19 @@ __device__ inline int real_roots_deg10(const double (&poly)[11], double (&roots)
     }
   }
   TV5_RTICK(7);
+  return ni;
+}
+
+// roots ascending; returns the count.  poly[0..10] ascending powers of w.
+__device__ inline int real_roots_deg10(const double (&poly)[11], double (&roots)[10]) {
+  FastChain s;
+  double back, ilo[10], ihi[10];
+  int ivlo[10];
+  const int ni = isolate_roots_deg10(poly, s, back, ilo, ihi, ivlo);
+  if (ni < 0) return real_roots_deg10_generic(poly, roots);
   for (int i = 0; i < ni; ++i)
-    roots[nr++] = ivlo[i] < 0 ? ilo[i] : fast_refine(s, ilo[i], ihi[i], ivlo[i]);
-  const double back = 1.0 / fac;
-  for (int i = 0; i < nr; ++i) roots[i] *= back;
-  return nr;
+    roots[i] = (ivlo[i] < 0 ? ilo[i] : fast_refine(s, ilo[i], ihi[i], ivlo[i])) * back;
+  return ni;
 }
 
 // ------------------------------------------------------------------------------------------

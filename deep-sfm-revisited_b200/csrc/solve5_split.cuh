@@ -1,0 +1,164 @@
+// solve5_split.cuh — the five-point solver as three kernels instead of one.
+//
+// The fused kernel (solve_sets) holds, per lane, the union of every phase's live state (255
+// registers, 8 warps per SM) and runs the two per-root phases — Newton refinement and E + pose —
+// as per-lane loops whose trip count is the warp's maximum root count (mean 4.6, maximum 10).
+// Here each phase is its own launch at its own register budget and lane mapping:
+//
+//   solve_front   lane = set (warp-cooperative constraints + elimination as before): null space,
+//                 10x20 system, 3x3 polynomial matrix, degree-10 determinant  -> record per set
+//   solve_roots   thread = set: Sturm chain, root isolation                  -> (set, interval) list
+//   solve_poses   thread = ROOT (compacted list, no divergence over the root count): bracketed
+//                 Newton, E from the root, twisted pair + cheirality, float32 hypothesis record
+//
+// Between the kernels a set is a 96-double record in global memory (written coalesced from shared
+// memory by solve_front, ~0.8 GB per 10^6 sets, read through L2).  Solutions are stored at their
+// ROOT index (ascending w) and a per-set bit mask says which ones survived; hypothesis ids carry
+// the root index, and the compacted index the C ABI promises is recovered by a popcount
+// (finalize) or by compact_solutions (tv5_solve5).
+#pragma once
+#include "solve5_coop.cuh"
+
+namespace tv5 {
+
+constexpr int kRecDoubles = 96;     // record per set
+constexpr int kRecB = 0;            // [36] null-space basis, k*9 + c
+constexpr int kRecBp = 36;          // [45] hidden-variable matrix, (r*3 + c)*5 + k
+constexpr int kRecPoly = 81;        // [11] determinant polynomial (solve_front: raw; solve_roots: monic, scaled)
+constexpr int kRecBack = 92;        // root of the scaled polynomial * back = w
+constexpr int kRecOk = 93;          // 1.0 when the set produced a polynomial
+
+struct RootEntry {                  // one isolated real root
+  double lo, hi;                    // bracket with a sign change (or lo = root when exact != 0)
+  int32_t set;                      // minimal set (hypothesis id) inside the image pair
+  int32_t r_exact;                  // root index | exact << 8
+};
+
+// ---- solve_front: grid (ceil(H/32), B), block 32 --------------------------------------------
+template <typename Gather>
+__device__ __forceinline__ void solve_front_warp(bool valid, const Gather& gather, double* __restrict__ rec_warp,
+                                                 int n_sets_here, double (*sB)[kCoopStride],
+                                                 double (*sR)[kCoopStride], int* sOk) {
+  const int lane = threadIdx.x & 31;
+  bool ok = valid;
+  {
+    double q[5][2], qp[5][2], B[4][9];
+    gather(q, qp);
+    nullspace_basis(q, qp, B);
+#pragma unroll
+    for (int c = 0; c < 9; ++c) ok = ok && (fabs(B[3][c]) <= 1.0);  // false on NaN (degenerate set)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 9; ++c) sB[k * 9 + c][lane] = ok ? B[k][c] : (k == 3 ? 1.0 : 0.0);
+  }
+  __syncwarp();
+  coop_constraints_eliminate(sB, sR, sOk, lane);
+  __syncwarp();
+  ok = ok && sOk[lane];
+  {
+    double Bp[3][3][5], poly[11];
+    hidden_matrix_from_rows(sR, lane, Bp);
+    hidden_determinant(Bp, poly);
+    // park Bp, poly and the flag in this lane's column of sR (its rows are consumed)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) sR[(r * 3 + c) * 5 + k][lane] = Bp[r][c][k];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) sR[45 + i][lane] = ok ? poly[i] : 0.0;
+    sR[56][lane] = 0.0;
+    sR[57][lane] = ok ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  // coalesced copy-out: lanes walk the 96 doubles of one record
+  for (int sidx = 0; sidx < n_sets_here; ++sidx) {
+    double* __restrict__ rec = rec_warp + (size_t)sidx * kRecDoubles;
+#pragma unroll
+    for (int e0 = 0; e0 < kRecDoubles; e0 += 32) {
+      const int e = e0 + lane;
+      double v = 0.0;
+      if (e < 36) v = sB[e][sidx];
+      else if (e < 36 + 58) v = sR[e - 36][sidx];
+      rec[e] = v;
+    }
+  }
+}
+
+// ---- solve_roots: one thread per set ----------------------------------------------------------
+// Returns the number of real roots; entries[0..n) receive the isolated roots in ascending order.
+__device__ inline int solve_roots_set(double* __restrict__ rec, RootEntry (&ent)[10]) {
+  if (!(rec[kRecOk] == 1.0)) return 0;
+  double poly[11];
+#pragma unroll
+  for (int i = 0; i < 11; ++i) poly[i] = rec[kRecPoly + i];
+  FastChain s;
+  double back, ilo[10], ihi[10];
+  int ivlo[10];
+  int ni = isolate_roots_deg10(poly, s, back, ilo, ihi, ivlo);
+  if (ni < 0) {  // generic chain (rare): roots come back refined, in w
+    double roots[10];
+    ni = real_roots_deg10_generic(poly, roots);
+    for (int i = 0; i < ni; ++i) { ent[i].lo = ent[i].hi = roots[i]; ent[i].r_exact = i | (1 << 8); }
+    rec[kRecBack] = 1.0;
+    return ni;
+  }
+  for (int i = 0; i < ni; ++i) {
+    double lo = ilo[i], hi = ihi[i], flo = 0.0;
+    int exact = 1;
+    if (ivlo[i] >= 0) exact = prepare_bracket(s, lo, hi, ivlo[i], flo);
+    ent[i].lo = lo;
+    ent[i].hi = exact ? lo : hi;
+    ent[i].r_exact = i | (exact << 8);
+  }
+  if (ni > 0) {
+#pragma unroll
+    for (int i = 0; i < 11; ++i) rec[kRecPoly + i] = s.c[0][i];
+    rec[kRecBack] = back;
+  }
+  return ni;
+}
+
+// ---- solve_poses: one thread per isolated root --------------------------------------------------
+// Returns true when the root gives a solution; E (and P when with_cheirality) are filled.
+template <typename Gather>
+__device__ inline bool solve_pose_root(const double* __restrict__ rec, const RootEntry& en, bool with_cheirality,
+                                       const Gather& gather, double (&E)[9], double (&P)[12]) {
+  double w;
+  if (en.r_exact >> 8) {
+    w = en.lo;
+  } else {
+    double p[11], dq[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) p[i] = rec[kRecPoly + i];
+#pragma unroll
+    for (int i = 1; i <= 10; ++i) dq[i - 1] = p[i] * i / 10.0;   // as fast_build (p is monic)
+    dq[10] = 0.0;
+    double f, d;
+    eval_p_dp(p, en.lo, f, d);
+    w = newton_bracketed(p, dq, en.lo, en.hi, f);
+  }
+  w *= rec[kRecBack];
+  double B[4][9], Bp[3][3][5];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int c = 0; c < 9; ++c) B[k][c] = rec[kRecB + k * 9 + c];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) Bp[r][c][k] = rec[kRecBp + (r * 3 + c) * 5 + k];
+  if (!essential_from_root(B, Bp, w, E)) return false;
+  if (with_cheirality) {
+    double q[5][2], qp[5][2];
+    gather(q, qp);
+    if (!pose_from_essential(E, q, qp, P)) return false;
+  }
+  return true;
+}
+
+}  // namespace tv5

@@ -23,6 +23,7 @@
 
 #include "solve5.cuh"
 #include "solve5_coop.cuh"
+#include "solve5_split.cuh"
 #include "polish.cuh"
 #include "flow_points.cuh"
 #include "plane_sweep.cuh"
@@ -250,6 +251,100 @@ __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ de
   if (!valid) return;
   n_valid[s] = nv;
   if (n_roots) n_roots[s] = nr;
+}
+
+// ------------------------------------------------------------------------------------------
+// split solver (solve5_split.cuh): solve_front -> solve_roots -> solve_poses
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) solve_front(const PairDesc* __restrict__ desc, int H,
+                                                  double* __restrict__ rec) {
+  __shared__ double sB[kCoopBasisDoubles][kCoopStride];
+  __shared__ double sR[kCoopRowsDoubles][kCoopStride];
+  __shared__ int sOk[32];
+  const int h_raw = blockIdx.x * 32 + threadIdx.x;
+  const bool valid = h_raw < H;
+  const int h = valid ? h_raw : H - 1;
+  const int b = blockIdx.y;
+  const PairDesc d = desc[b];
+  const GatherSet gather{d, h};
+  solve_front_warp(valid, gather, rec + ((size_t)b * H + (size_t)blockIdx.x * 32) * kRecDoubles,
+                   min(32, H - (int)blockIdx.x * 32), sB, sR, sOk);
+}
+
+__global__ void __launch_bounds__(64) solve_roots(PairState* __restrict__ state, int H,
+                                                  double* __restrict__ rec, RootEntry* __restrict__ entries,
+                                                  int32_t* __restrict__ n_roots, int32_t* __restrict__ valid_mask) {
+  const int h = blockIdx.x * 64 + threadIdx.x;
+  if (h >= H) return;
+  const int b = blockIdx.y;
+  const size_t s = (size_t)b * H + h;
+  RootEntry ent[10];
+  const int n = solve_roots_set(rec + s * kRecDoubles, ent);
+  if (n_roots) n_roots[s] = n;
+  valid_mask[s] = 0;
+  if (n > 0) {
+    const int base = atomicAdd(&state[b].n_entries, n);
+    RootEntry* __restrict__ dst = entries + (size_t)b * H * 10 + base;
+    for (int i = 0; i < n; ++i) {
+      ent[i].set = h;
+      dst[i] = ent[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) solve_poses(const PairDesc* __restrict__ desc, PairState* __restrict__ state,
+                                                   int H, int with_cheirality, const double* __restrict__ rec,
+                                                   const RootEntry* __restrict__ entries,
+                                                   double* __restrict__ E_list, double* __restrict__ P_list,
+                                                   int32_t* __restrict__ valid_mask, Hyp32* __restrict__ hyp,
+                                                   int32_t* __restrict__ hyp_id, uint32_t* __restrict__ notin,
+                                                   uint32_t* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= state[b].n_entries) return;
+  const RootEntry en = entries[(size_t)b * H * 10 + e];
+  const size_t s = (size_t)b * H + en.set;
+  const int r = en.r_exact & 255;
+  const PairDesc d = desc[b];
+  const GatherSet gather{d, en.set};
+  double E[9], P[12];
+  if (!solve_pose_root(rec + s * kRecDoubles, en, with_cheirality != 0, gather, E, P)) return;
+#pragma unroll
+  for (int c = 0; c < 9; ++c) E_list[s * 90 + r * 9 + c] = E[c];
+  if (P_list && with_cheirality) {
+#pragma unroll
+    for (int c = 0; c < 12; ++c) P_list[s * 120 + r * 12 + c] = P[c];
+  }
+  atomicOr(&valid_mask[s], 1 << r);
+  if (hyp) {
+    const int slot = atomicAdd(&state[b].M, 1);
+    const size_t o = (size_t)b * H * 10 + slot;
+    Hyp32 rcd;
+    make_hyp32(E, state[b].s_scale, rcd);
+    hyp[o] = rcd;
+    hyp_id[o] = en.set * 16 + r;
+    notin[o] = 0u;
+    out[o] = 0u;
+  }
+}
+
+// tv5_solve5: solutions stored at their root index -> lists compacted to the valid ones
+__global__ void compact_solutions(int n_sets, double* __restrict__ E_list, double* __restrict__ P_list,
+                                  int32_t* __restrict__ mask_to_count) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sets) return;
+  const unsigned m = (unsigned)mask_to_count[s];
+  int j = 0;
+  for (int r = 0; r < 10; ++r) {
+    if (!((m >> r) & 1u)) continue;
+    if (j != r) {
+      for (int c = 0; c < 9; ++c) { E_list[(size_t)s * 90 + j * 9 + c] = E_list[(size_t)s * 90 + r * 9 + c]; E_list[(size_t)s * 90 + r * 9 + c] = 0.0; }
+      if (P_list)
+        for (int c = 0; c < 12; ++c) { P_list[(size_t)s * 120 + j * 12 + c] = P_list[(size_t)s * 120 + r * 12 + c]; P_list[(size_t)s * 120 + r * 12 + c] = 0.0; }
+    }
+    ++j;
+  }
+  mask_to_count[s] = j;
 }
 
 // float32 hypothesis records for an arbitrary E list (tv5_score_bounds)
@@ -539,7 +634,8 @@ __global__ void __launch_bounds__(256) finalize(const PairDesc* __restrict__ des
                                                 const double* __restrict__ P_list,
                                                 const int32_t* __restrict__ hyp_id,
                                                 const int32_t* __restrict__ cand,
-                                                const int32_t* __restrict__ cand_cnt) {
+                                                const int32_t* __restrict__ cand_cnt,
+                                                const int32_t* __restrict__ valid_mask) {
   const int b = blockIdx.x;
   const PairDesc d = desc[b];
   const PairState& s = state[b];
@@ -577,7 +673,10 @@ __global__ void __launch_bounds__(256) finalize(const PairDesc* __restrict__ des
     tv5_result r;
     r.count = count;
     r.best_set = have ? (id >> 4) : -1;
-    r.best_root = have ? (id & 15) : -1;
+    // split solver: ids carry the root index; the compacted index counts the valid roots below it
+    int root = id & 15;
+    if (have && valid_mask) root = __popc((unsigned)valid_mask[(size_t)b * H + (id >> 4)] & ((1u << root) - 1u));
+    r.best_root = have ? root : -1;
     r.n_hypotheses = s.M;
     r.n_candidates = s.n_cand;
     r.fast_path = s.fast;
@@ -790,6 +889,12 @@ static int ensure_workspace(tv5_ctx* ctx, int B, size_t total_pp, size_t total_s
     if ((rc = grow_same(ctx, w.P_list, w.sets_cap * 120, nc * 120))) return rc;
     if ((rc = grow_same(ctx, w.n_valid, w.sets_cap, nc))) return rc;
     if ((rc = grow_same(ctx, w.n_roots, w.sets_cap, nc))) return rc;
+    if ((rc = grow_same(ctx, w.rec, w.sets_cap * kRecDoubles, nc * kRecDoubles))) return rc;
+    {
+      RootEntry* en = (RootEntry*)w.entries;
+      if ((rc = grow_same(ctx, en, w.sets_cap * 10, nc * 10))) { w.entries = nullptr; return rc; }
+      w.entries = en;
+    }
     if ((rc = grow_same(ctx, w.hyp, w.sets_cap * 10, nc * 10))) return rc;
     if ((rc = grow_same(ctx, w.hyp_id, w.sets_cap * 10, nc * 10))) return rc;
     if ((rc = grow_same(ctx, w.notin, w.sets_cap * 10, nc * 10))) return rc;
@@ -921,7 +1026,7 @@ int tv5_destroy(tv5_ctx* ctx) {
   if (!ctx) return TV5_OK;
   cudaSetDevice(ctx->device);
   Workspace& w = ctx->ws;
-  void* ptrs[] = {w.desc, w.state, w.ctl, w.pp, w.E_list, w.P_list, w.n_valid, w.n_roots, w.hyp,
+  void* ptrs[] = {w.desc, w.state, w.ctl, w.pp, w.E_list, w.P_list, w.n_valid, w.n_roots, w.rec, w.entries, w.hyp,
                   w.hyp_id, w.notin, w.out, w.cand, w.cand_cnt, w.h2d_x, w.h2d_sets, w.out_E,
                   w.out_P, w.out_res, w.polish_jobs, w.polish_partial, w.polish_barrier,
                   w.polish_x, w.polish_E, w.flow_jobs, w.flow_x, w.flow_EP};
@@ -1077,9 +1182,20 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
     band_consts<<<(nb + 127) / 128, 128, 0, s_front>>>(desc, state, nb, thr, allow_fast);
     if (allow_fast) prep_points<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_front>>>(desc, state, w.pp);
     if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 1], s_front);
-    solve_sets<<<dim3((H + 31) / 32, nb), 32, 0, s_front>>>(
-        desc, state, H, with_cheirality, w.E_list + so * 90, with_cheirality ? w.P_list + so * 120 : nullptr,
-        w.n_valid + so, w.n_roots + so, w.hyp + so * 10, w.hyp_id + so * 10, w.notin + so * 10, w.out + so * 10);
+    if (ctx->split_solver) {
+      solve_front<<<dim3((H + 31) / 32, nb), 32, 0, s_front>>>(desc, H, w.rec + so * kRecDoubles);
+      solve_roots<<<dim3((H + 63) / 64, nb), 64, 0, s_front>>>(state, H, w.rec + so * kRecDoubles,
+                                                               (RootEntry*)w.entries + so * 10, w.n_roots + so,
+                                                               w.n_valid + so);
+      solve_poses<<<dim3((H * 10 + 127) / 128, nb), 128, 0, s_front>>>(
+          desc, state, H, with_cheirality, w.rec + so * kRecDoubles, (const RootEntry*)w.entries + so * 10,
+          w.E_list + so * 90, with_cheirality ? w.P_list + so * 120 : nullptr, w.n_valid + so, w.hyp + so * 10,
+          w.hyp_id + so * 10, w.notin + so * 10, w.out + so * 10);
+    } else {
+      solve_sets<<<dim3((H + 31) / 32, nb), 32, 0, s_front>>>(
+          desc, state, H, with_cheirality, w.E_list + so * 90, with_cheirality ? w.P_list + so * 120 : nullptr,
+          w.n_valid + so, w.n_roots + so, w.hyp + so * 10, w.hyp_id + so * 10, w.notin + so * 10, w.out + so * 10);
+    }
     if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 2], s_front);
     if (two_streams) TV5_CUDA(ctx, cudaEventRecord(ctx->pipe_solved[c], s_front));
     return TV5_OK;
@@ -1141,7 +1257,8 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
       }
     }
     if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 6], s_back);
-    finalize<<<nb, 256, 0, s_back>>>(desc, state, H, thr, E_list, P_list, hyp_id, cand, cand_cnt);
+    finalize<<<nb, 256, 0, s_back>>>(desc, state, H, thr, E_list, P_list, hyp_id, cand, cand_cnt,
+                                     ctx->split_solver ? w.n_valid + so : nullptr);
     if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 7], s_back);
     return TV5_OK;
   };
@@ -1256,9 +1373,23 @@ int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, i
   TV5_CUDA(ctx, cudaMemcpyAsync(ctx->ws.desc, &d, sizeof(d), cudaMemcpyHostToDevice, st));
   TV5_CUDA(ctx, cudaMemsetAsync(E_list, 0, (size_t)H * 90 * sizeof(double), st));
   if (P_list) TV5_CUDA(ctx, cudaMemsetAsync(P_list, 0, (size_t)H * 120 * sizeof(double), st));
-  solve_sets<<<dim3((H + 31) / 32, 1), 32, 0, st>>>(ctx->ws.desc, ctx->ws.state, H, with_cheirality,
-                                                   E_list, with_cheirality ? P_list : nullptr, n_valid,
-                                                   n_roots, nullptr, nullptr, nullptr, nullptr);
+  if (ctx->split_solver) {
+    Workspace& w = ctx->ws;
+    if ((rc = ensure_workspace(ctx, 1, 1, (size_t)H))) return rc;
+    TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+    TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState), st));
+    solve_front<<<dim3((H + 31) / 32, 1), 32, 0, st>>>(w.desc, H, w.rec);
+    solve_roots<<<dim3((H + 63) / 64, 1), 64, 0, st>>>(w.state, H, w.rec, (RootEntry*)w.entries, n_roots, n_valid);
+    solve_poses<<<dim3((H * 10 + 127) / 128, 1), 128, 0, st>>>(w.desc, w.state, H, with_cheirality, w.rec,
+                                                              (const RootEntry*)w.entries, E_list,
+                                                              with_cheirality ? P_list : nullptr, n_valid, nullptr,
+                                                              nullptr, nullptr, nullptr);
+    compact_solutions<<<(H + 127) / 128, 128, 0, st>>>(H, E_list, with_cheirality ? P_list : nullptr, n_valid);
+  } else {
+    solve_sets<<<dim3((H + 31) / 32, 1), 32, 0, st>>>(ctx->ws.desc, ctx->ws.state, H, with_cheirality,
+                                                     E_list, with_cheirality ? P_list : nullptr, n_valid,
+                                                     n_roots, nullptr, nullptr, nullptr, nullptr);
+  }
   TV5_CUDA(ctx, cudaGetLastError());
   return TV5_OK;
 }
@@ -1588,6 +1719,12 @@ int tv5_measure_fp32_peak(tv5_ctx* ctx, int mode, double* tflops_out) {
 int tv5_set_force_exact(tv5_ctx* ctx, int on) {
   if (!ctx) return TV5_ERR_INVALID;
   ctx->force_exact = on != 0;
+  return TV5_OK;
+}
+
+int tv5_set_split_solver(tv5_ctx* ctx, int on) {
+  if (!ctx) return TV5_ERR_INVALID;
+  ctx->split_solver = on != 0;
   return TV5_OK;
 }
 

@@ -58,6 +58,8 @@ struct PairState {
   int32_t n_hc, n_pc;     // tiles = hypothesis chunks x point chunks
   int32_t n_cand;         // hypotheses to re-score exactly (atomic)
   int32_t exact_from;     // first candidate not yet re-scored
+  int32_t n_entries;      // isolated real roots of the pair (split solver, atomic)
+  int32_t pad2;
   double s_scale;         // sqrt(1-c)/thr folded into the float32 point / hypothesis records
   BandConst band;
 };
@@ -77,6 +79,8 @@ struct Workspace {
   double* P_list = nullptr;                           // [B*H,10,12]
   int32_t* n_valid = nullptr;                         // [B*H]
   int32_t* n_roots = nullptr;                         // [B*H]
+  double* rec = nullptr;                              // [B*H,96]  split solver: record per set
+  void* entries = nullptr;                            // [B*H*10]  split solver: isolated roots (RootEntry)
   Hyp32* hyp = nullptr;      size_t hyp_cap = 0;      // [B*H*10]
   int32_t* hyp_id = nullptr;                          // [B*H*10]  set*16 + root
   uint32_t* notin = nullptr;                          // [B*H*10]
@@ -122,6 +126,7 @@ struct tv5_ctx {
   cudaEvent_t start_ev = nullptr;
   int polish_max_ctas = 0;              // co-resident CTAs of irls_polish on this device
   // solver / scorer overlap inside one submission
+  bool split_solver = true;             // three-kernel solver (solve5_split.cuh) instead of solve_sets
   bool overlap = false;
   bool profiling_serial = false;
   cudaStream_t front_stream = nullptr;  // prep + solve, least priority

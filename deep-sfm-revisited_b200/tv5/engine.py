@@ -426,6 +426,10 @@ class Engine:
     def set_force_exact(self, on=True):
         _check(self.ctx, self.L.tv5_set_force_exact(self.ctx, int(bool(on))), "set_force_exact")
 
+    def set_split_solver(self, on=True):
+        """Three-kernel solver (default) vs the fused kernel; results do not depend on it."""
+        _check(self.ctx, self.L.tv5_set_split_solver(self.ctx, int(bool(on))), "set_split_solver")
+
     def set_overlap(self, on=True):
         """Solver/scorer overlap inside one submission (default off); results do not depend on it."""
         _check(self.ctx, self.L.tv5_set_overlap(self.ctx, int(bool(on))), "set_overlap")

@@ -261,6 +261,11 @@ int tv5_plane_sweep(tv5_ctx* ctx, void* stream, const float* ref_feat, const flo
  * tests use this to prove it. */
 int tv5_set_force_exact(tv5_ctx* ctx, int on);
 
+/* Five-point solver organisation: on != 0 (default) = three kernels (front: null space + elimination +
+ * determinant per set; roots: Sturm isolation per set; poses: Newton + E + cheirality per ROOT), on = 0 =
+ * the fused one-kernel form.  Results are identical (tested); only the speed differs. */
+int tv5_set_split_solver(tv5_ctx* ctx, int on);
+
 /* Solver/scorer overlap (experimental, default off): a submission of >= 32 pairs is cut into up
  * to 8 chunks whose five-point solve runs on a low-priority internal stream concurrently with the
  * scoring of the previous chunk on a high-priority one; results are identical either way.

@@ -703,3 +703,26 @@ def test_scoring_random_property_counts_equal_oracle(engine, seed):
         return                                      # band too wide for float32: the pipeline uses float64
     lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
     assert (lo <= c_or).all() and (c_or <= hi).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# solver organisation: three kernels (default) vs the fused kernel
+# ---------------------------------------------------------------------------------------------
+def test_split_solver_is_bit_identical_to_fused_solver(engine, std_pair):
+    sc, x1, x2 = std_pair
+    sets = dev(synth.make_sets(10000, 4096, 77), torch.int32)
+    try:
+        engine.set_split_solver(False)
+        f = engine.solve5(x1, x2, sets, True)
+        f0 = engine.solve5(x1, x2, sets, False)
+        rf = engine.compute_pose(x1, x2, 8, THR, sets=sets, want_mask=True)
+    finally:
+        engine.set_split_solver(True)
+    s = engine.solve5(x1, x2, sets, True)
+    s0 = engine.solve5(x1, x2, sets, False)
+    rs = engine.compute_pose(x1, x2, 8, THR, sets=sets, want_mask=True)
+    for a, b in ((f, s), (f0, s0)):
+        for k in ("E", "P", "n_roots", "n_valid"):
+            assert torch.equal(a[k], b[k]), k          # same arithmetic sequence per root: bit-identical
+    assert torch.equal(rf.E, rs.E) and torch.equal(rf.P, rs.P) and torch.equal(rf.mask, rs.mask)
+    assert torch.equal(rf.stats[:5], rs.stats[:5])      # count, set, (compacted) root, M, candidates
