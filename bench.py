@@ -31,8 +31,8 @@ H = 512 * ITERS
 THR = 1e-4
 PAIRS_PER_GPU = 256
 FLOP_PER_EVAL = 34        # 15 FMA + 3 MUL + 1 compare
-KERNELS_PER_STEP = 11     # prep_norms, band_consts, prep_points, solve_sets, plan_tiles, score_bounds,
-                          # pick_top, exact_counts, pick_rest, exact_counts, finalize
+KERNELS_PER_STEP = 13     # prep_norms, band_consts, prep_points, solve_front, solve_roots, solve_poses, plan_tiles,
+                          # score_bounds, pick_top, exact_counts, pick_rest, exact_counts, finalize
 METRIC = "two-view E+pose pair-solves/s @10k corr x 4096 hyp"
 UNIT = "pairs/s"
 

@@ -24,9 +24,10 @@ namespace tv5 {
 constexpr int kRecDoubles = 96;     // record per set
 constexpr int kRecB = 0;            // [36] null-space basis, k*9 + c
 constexpr int kRecBp = 36;          // [45] hidden-variable matrix, (r*3 + c)*5 + k
-constexpr int kRecPoly = 81;        // [11] determinant polynomial (solve_front: raw; solve_roots: monic, scaled)
-constexpr int kRecBack = 92;        // root of the scaled polynomial * back = w
-constexpr int kRecOk = 93;          // 1.0 when the set produced a polynomial
+constexpr int kRecPoly = 82;        // [11] determinant polynomial (solve_front: raw; solve_roots: monic, scaled)
+constexpr int kRecBack = 93;        // root of the scaled polynomial * back = w
+constexpr int kRecOk = 94;          // 1.0 when the set produced a polynomial
+// (offsets are even so that every field can be read with 16-byte loads)
 
 struct RootEntry {                  // one isolated real root
   double lo, hi;                    // bracket with a sign change (or lo = root when exact != 0)
@@ -67,10 +68,11 @@ __device__ __forceinline__ void solve_front_warp(bool valid, const Gather& gathe
       for (int c = 0; c < 3; ++c)
 #pragma unroll
         for (int k = 0; k < 5; ++k) sR[(r * 3 + c) * 5 + k][lane] = Bp[r][c][k];
+    sR[45][lane] = 0.0;
 #pragma unroll
-    for (int i = 0; i < 11; ++i) sR[45 + i][lane] = ok ? poly[i] : 0.0;
-    sR[56][lane] = 0.0;
-    sR[57][lane] = ok ? 1.0 : 0.0;
+    for (int i = 0; i < 11; ++i) sR[46 + i][lane] = ok ? poly[i] : 0.0;
+    sR[57][lane] = 0.0;
+    sR[58][lane] = ok ? 1.0 : 0.0;
   }
   __syncwarp();
   // coalesced copy-out: lanes walk the 96 doubles of one record
@@ -81,7 +83,7 @@ __device__ __forceinline__ void solve_front_warp(bool valid, const Gather& gathe
       const int e = e0 + lane;
       double v = 0.0;
       if (e < 36) v = sB[e][sidx];
-      else if (e < 36 + 58) v = sR[e - 36][sidx];
+      else if (e < 36 + 59) v = sR[e - 36][sidx];
       rec[e] = v;
     }
   }
@@ -126,32 +128,41 @@ __device__ inline int solve_roots_set(double* __restrict__ rec, RootEntry (&ent)
 template <typename Gather>
 __device__ inline bool solve_pose_root(const double* __restrict__ rec, const RootEntry& en, bool with_cheirality,
                                        const Gather& gather, double (&E)[9], double (&P)[12]) {
+  const double2* __restrict__ rec2 = reinterpret_cast<const double2*>(rec);
   double w;
   if (en.r_exact >> 8) {
-    w = en.lo;
+    w = en.lo * rec[kRecBack];
   } else {
-    double p[11], dq[11];
+    double p[12], dq[11];
 #pragma unroll
-    for (int i = 0; i < 11; ++i) p[i] = rec[kRecPoly + i];
+    for (int i = 0; i < 6; ++i) {
+      const double2 v = rec2[kRecPoly / 2 + i];     // poly[0..10], back
+      p[2 * i] = v.x; p[2 * i + 1] = v.y;
+    }
+    const double (&pp)[11] = *reinterpret_cast<const double (*)[11]>(&p[0]);
 #pragma unroll
     for (int i = 1; i <= 10; ++i) dq[i - 1] = p[i] * i / 10.0;   // as fast_build (p is monic)
     dq[10] = 0.0;
     double f, d;
-    eval_p_dp(p, en.lo, f, d);
-    w = newton_bracketed(p, dq, en.lo, en.hi, f);
+    eval_p_dp(pp, en.lo, f, d);
+    w = newton_bracketed(pp, dq, en.lo, en.hi, f) * p[11];
   }
-  w *= rec[kRecBack];
   double B[4][9], Bp[3][3][5];
+  {
+    double* Bf = &B[0][0];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+    for (int i = 0; i < 18; ++i) {
+      const double2 v = rec2[kRecB / 2 + i];
+      Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y;
+    }
+    double* Pf = &Bp[0][0][0];
 #pragma unroll
-    for (int c = 0; c < 9; ++c) B[k][c] = rec[kRecB + k * 9 + c];
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int k = 0; k < 5; ++k) Bp[r][c][k] = rec[kRecBp + (r * 3 + c) * 5 + k];
+    for (int i = 0; i < 22; ++i) {
+      const double2 v = rec2[kRecBp / 2 + i];
+      Pf[2 * i] = v.x; Pf[2 * i + 1] = v.y;
+    }
+    Pf[44] = rec[kRecBp + 44];
+  }
   if (!essential_from_root(B, Bp, w, E)) return false;
   if (with_cheirality) {
     double q[5][2], qp[5][2];
