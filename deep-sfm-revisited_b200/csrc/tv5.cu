@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(64) solve_roots(PairState* __restrict__ state,
   }
 }
 
-__global__ void __launch_bounds__(128) solve_poses(const PairDesc* __restrict__ desc, PairState* __restrict__ state,
+__global__ void __launch_bounds__(128, 4) solve_poses(const PairDesc* __restrict__ desc, PairState* __restrict__ state,
                                                    int H, int with_cheirality, const double* __restrict__ rec,
                                                    const RootEntry* __restrict__ entries,
                                                    double* __restrict__ E_list, double* __restrict__ P_list,
