@@ -1146,7 +1146,8 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
   //    (DESIGN.md section 4.4): no gain — solver warps make almost no progress next to the
   //    FFMA2-saturating scorer — hence off by default.
   int n_chunks = 1;
-  if ((ctx->overlap || ready_ev) && !two_stage) n_chunks = std::max(1, std::min(kPipeChunks, B / kPipeMinPairs));
+  if (ready_ev && !two_stage) n_chunks = n_ready;        // compute chunks = copy chunks
+  else if (ctx->overlap && !two_stage) n_chunks = std::max(1, std::min(kPipeChunks, B / kPipeMinPairs));
   const bool two_streams = ctx->overlap && n_chunks > 1;
   cudaStream_t s_front = st, s_back = st;
   if (two_streams) {
@@ -1158,7 +1159,8 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
     TV5_CUDA(ctx, cudaStreamWaitEvent(s_back, ctx->pipe_entry, 0));
   }
   std::vector<int> first((size_t)n_chunks + 1);
-  for (int c = 0; c <= n_chunks; ++c) first[c] = (int)((int64_t)B * c / n_chunks);
+  for (int c = 0; c <= n_chunks; ++c)
+    first[c] = (ready_ev && n_chunks == n_ready) ? ready_first[c] : (int)((int64_t)B * c / n_chunks);
   const int slots = TV5_SCORE_MINB * ctx->sm_count;
   const bool prof = ctx->profiling;
   if (prof && (rc = ensure_prof_events(ctx, n_chunks))) return rc;
@@ -1324,15 +1326,20 @@ int tv5_compute_pose_batch_host(tv5_ctx* ctx, void* stream, int B, const double*
     for (auto& e : ctx->chunk_ev) TV5_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     TV5_CUDA(ctx, cudaEventCreateWithFlags(&ctx->start_ev, cudaEventDisableTiming));
   }
-  // Pipeline: the batch is cut into up to kHostChunks chunks of pairs; the host->device copies of
-  // chunk k+1 (own stream) overlap the kernels of chunk k (caller's stream).
-  const int n_chunks = std::min(kHostChunks, B);
+  // Pipeline: the batch is cut into chunks of pairs; the host->device copies of chunk k+1 (own
+  // stream) overlap the kernels of chunk k (caller's stream).  The copies are ~10x faster than the
+  // kernels, so the chunks grow geometrically (1/16, 3/16, 3/4 of the batch): the first kernels
+  // start after 1/16 of the copy time and only three launches of each kernel are made.
+  std::vector<int> first;
+  first.push_back(0);
+  if (B >= 64) { first.push_back(B / 16); first.push_back(B / 4); }
+  else if (B >= 2) first.push_back(B / 2);
+  first.push_back(B);
+  const int n_chunks = (int)first.size() - 1;
   double* dx1 = w.h2d_x;
   double* dx2 = w.h2d_x + total * 2;
   TV5_CUDA(ctx, cudaEventRecord(ctx->start_ev, st));
   TV5_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->start_ev, 0));
-  std::vector<int> first(n_chunks + 1);
-  for (int k = 0; k <= n_chunks; ++k) first[k] = (int)((int64_t)B * k / n_chunks);
   for (int k = 0; k < n_chunks; ++k) {
     const int b0 = first[k], b1 = first[k + 1];
     const size_t p0 = (size_t)(pt_offsets[b0] - pt_offsets[0]), np = (size_t)(pt_offsets[b1] - pt_offsets[b0]);
