@@ -1501,6 +1501,7 @@ int tv5_optimise_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, cons
                        const int64_t* pt_offsets, const uint8_t* mask, double* E_io, double delta,
                        double alpha, int max_reps, int32_t* iters_out) {
   if (!ctx || B < 1 || !pt_offsets || !E_io || max_reps < 0) return TV5_ERR_INVALID;
+  max_reps = std::min(max_reps, 1000000);   // keeps the monotonic barrier counter (reps x CTAs) inside 32 bits
   cudaStream_t st = (cudaStream_t)stream;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!ctx->polish_max_ctas) {

@@ -183,7 +183,9 @@ int tv5_decompose_batch(tv5_ctx* ctx, void* stream, const double* E, int B, doub
  * angles; replaces EssentialMatrixOptimise (essential_matrix.cu:76-105 ->
  * polish_E_robust_parametric, polish_E.cu:1470-1577; Python `optimise`), which the reference
  * runs on one CPU core.  Residual e = (V^T x1)_0 (U^T x2)_0 + (V^T x1)_1 (U^T x2)_1, weight 1 if
- * |e| < delta else alpha*delta/|e|; stops when |J^T W e|^2 < 1e-20 or after max_reps updates.
+ * |e| < delta else alpha*delta/|e|; stops when |J^T W e|^2 < 1e-20 or after max_reps updates
+ * (max_reps is clamped to 1,000,000).  Like the reference, a call that stops before its first
+ * update returns the half-reduced working matrix of the decomposition (polish_E.cu:1545).
  *   x1, x2     device [N,2] float64
  *   mask       device [N] uint8 or NULL; points with mask == 0 are ignored (extension: lets the
  *              winner's inlier mask of tv5_compute_pose drive a local-optimisation step)
