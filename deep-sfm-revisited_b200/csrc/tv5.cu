@@ -377,7 +377,9 @@ __global__ void __launch_bounds__(1024) plan_tiles(const PairDesc* __restrict__ 
     int tiles = 0;
     if (b < B) {
       PairState& s = state[b];
-      const int npp = (desc[b].n_full + 1) >> 1;
+      const int npp_all = (desc[b].n_full + 1) >> 1;
+      if (s.pp_hi <= 0) { s.pp_lo = 0; s.pp_hi = npp_all; }   // no staging: the whole pair
+      const int npp = max(0, min(s.pp_hi, npp_all) - s.pp_lo);
       s.n_hc = (s.M + kHypChunk - 1) / kHypChunk;
       s.n_pc = (npp + pp_per_tile - 1) / pp_per_tile;
       tiles = s.fast ? s.n_hc * s.n_pc : 0;
@@ -449,8 +451,8 @@ score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ st
     const int lt = t - s.tile_start;
     const int hc = lt / s.n_pc, pc = lt - hc * s.n_pc;
     const int npp_all = (d.n_full + 1) >> 1;
-    const int pp0 = pc * pp_per_tile;
-    const int npp = min(pp_per_tile, npp_all - pp0);
+    const int pp0 = s.pp_lo + pc * pp_per_tile;
+    const int npp = min(pp_per_tile, min(s.pp_hi, npp_all) - pp0);
     if (tid == 0) {
       const uint32_t bytes = (uint32_t)npp * (uint32_t)sizeof(PointPair32);
       mbar_expect_tx(&bar, bytes);
@@ -507,6 +509,101 @@ score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ st
       }
     __syncthreads();  // everyone is done with `tile` and `s_tile` before the next round
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Early exit (opt-in): the points are scored in stages; after a stage every hypothesis whose
+// upper bound on the FULL count — points not yet seen counted as inliers — is below the exact
+// count L of an actual hypothesis can no longer win and is dropped before the next stage.
+//   set_stage      point-pair range of the next stage (fractions of each pair's points)
+//   stage_leader   hypothesis with the fewest sure outliers so far -> cand[0] (exact_counts -> L)
+//   prune_compact  survivors (out <= n - L) copied to the ping-pong arrays, M := survivor count
+// Exactness: `out` counts evaluations that are outliers under every rounding (guard band), so
+// n - out is a rigorous upper bound; a dropped hypothesis has count <= n - out < L <= winner.
+// ------------------------------------------------------------------------------------------
+__global__ void set_stage(const PairDesc* __restrict__ desc, PairState* __restrict__ state, int B,
+                          float f_lo, float f_hi, int first, int pp_per_tile) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int npp = (desc[b].n_full + 1) >> 1;
+  // stage boundaries on whole scoring tiles (64 point pairs for small inputs); the last stage
+  // ends at the end
+  const int q = npp >= 4 * pp_per_tile ? pp_per_tile : 64;
+  const int lo = f_lo <= 0.f ? 0 : min(npp, (((int)(f_lo * npp) + q / 2) / q) * q);
+  const int hi = f_hi >= 1.f ? npp : min(npp, (((int)(f_hi * npp) + q / 2) / q) * q);
+  state[b].pp_lo = lo;
+  state[b].pp_hi = max(hi, lo);
+  if (first) state[b].M_total = state[b].M;
+}
+
+__global__ void __launch_bounds__(256) stage_leader(const PairDesc* __restrict__ desc,
+                                                    PairState* __restrict__ state, int H,
+                                                    const uint32_t* __restrict__ out,
+                                                    const int32_t* __restrict__ hyp_id,
+                                                    int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
+  const int b = blockIdx.x;
+  PairState& s = state[b];
+  const int M = s.M;
+  const size_t base = (size_t)b * H * 10;
+  if (threadIdx.x == 0) { cand_cnt[base] = 0; s.exact_from = 0; }
+  if (!s.fast || M == 0) {  // float64 pairs are not staged: nothing to score, nothing will be pruned
+    if (threadIdx.x == 0) s.n_cand = 0;
+    return;
+  }
+  __shared__ unsigned long long s_key[8];
+  unsigned long long key = 0ull;  // (fewest sure outliers, smallest id) as a maximum
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const unsigned long long k = ((unsigned long long)(0xFFFFFFFFu - out[base + m]) << 32) |
+                                 (0xFFFFFFFFu - (uint32_t)hyp_id[base + m]);
+    key = k > key ? k : key;
+  }
+  key = warp_max(key);
+  if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
+  __syncthreads();
+  unsigned long long best = 0ull;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) best = s_key[w] > best ? s_key[w] : best;
+  const int best_id = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
+  if (threadIdx.x == 0) s.n_cand = 1;
+  for (int m = threadIdx.x; m < M; m += blockDim.x)
+    if (hyp_id[base + m] == best_id) cand[base] = m;
+}
+
+__global__ void __launch_bounds__(256) prune_compact(const PairDesc* __restrict__ desc,
+                                                     PairState* __restrict__ state, int H,
+                                                     const Hyp32* __restrict__ hyp, const int32_t* __restrict__ hyp_id,
+                                                     const uint32_t* __restrict__ out,
+                                                     const int32_t* __restrict__ cand_cnt,
+                                                     Hyp32* __restrict__ hyp_dst, int32_t* __restrict__ id_dst,
+                                                     uint32_t* __restrict__ out_dst) {
+  const int b = blockIdx.x;
+  PairState& s = state[b];
+  const size_t base = (size_t)b * H * 10;
+  const int M = s.M;
+  const int n = desc[b].n_full;
+  const int L = cand_cnt[base];                       // exact full count of the stage leader
+  const uint32_t max_out = (uint32_t)max(n - L, 0);  // survive iff n - out >= L
+  __shared__ int s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  for (int m0 = 0; m0 < M; m0 += blockDim.x) {
+    const int m = m0 + threadIdx.x;
+    const bool keep = m < M && (!s.fast || out[base + m] <= max_out);
+    // block-wide compaction: ballot per warp, one shared-memory atomic per warp
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31;
+    int wbase = 0;
+    if (lane == 0 && bal) wbase = atomicAdd(&s_count, __popc(bal));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (keep) {
+      const int dst = wbase + __popc(bal & ((1u << lane) - 1u));
+      hyp_dst[base + dst] = hyp[base + m];
+      id_dst[base + dst] = hyp_id[base + m];
+      out_dst[base + dst] = out[base + m];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s.M = s_count;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -677,7 +774,7 @@ __global__ void __launch_bounds__(256) finalize(const PairDesc* __restrict__ des
     int root = id & 15;
     if (have && valid_mask) root = __popc((unsigned)valid_mask[(size_t)b * H + (id >> 4)] & ((1u << root) - 1u));
     r.best_root = have ? root : -1;
-    r.n_hypotheses = s.M;
+    r.n_hypotheses = s.M_total > 0 ? s.M_total : s.M;
     r.n_candidates = s.n_cand;
     r.fast_path = s.fast;
     r.reserved[0] = r.reserved[1] = 0;
@@ -899,6 +996,9 @@ static int ensure_workspace(tv5_ctx* ctx, int B, size_t total_pp, size_t total_s
     if ((rc = grow_same(ctx, w.hyp_id, w.sets_cap * 10, nc * 10))) return rc;
     if ((rc = grow_same(ctx, w.notin, w.sets_cap * 10, nc * 10))) return rc;
     if ((rc = grow_same(ctx, w.out, w.sets_cap * 10, nc * 10))) return rc;
+    if ((rc = grow_same(ctx, w.hyp2, w.sets_cap * 10, nc * 10))) return rc;
+    if ((rc = grow_same(ctx, w.hyp_id2, w.sets_cap * 10, nc * 10))) return rc;
+    if ((rc = grow_same(ctx, w.out2, w.sets_cap * 10, nc * 10))) return rc;
     if ((rc = grow_same(ctx, w.cand, w.sets_cap * 30, nc * 30))) return rc;  // + 2x set_winners scratch
     if ((rc = grow_same(ctx, w.cand_cnt, w.sets_cap * 10, nc * 10))) return rc;
     w.sets_cap = nc;
@@ -1027,7 +1127,7 @@ int tv5_destroy(tv5_ctx* ctx) {
   cudaSetDevice(ctx->device);
   Workspace& w = ctx->ws;
   void* ptrs[] = {w.desc, w.state, w.ctl, w.pp, w.E_list, w.P_list, w.n_valid, w.n_roots, w.rec, w.entries, w.hyp,
-                  w.hyp_id, w.notin, w.out, w.cand, w.cand_cnt, w.h2d_x, w.h2d_sets, w.out_E,
+                  w.hyp_id, w.notin, w.out, w.hyp2, w.hyp_id2, w.out2, w.cand, w.cand_cnt, w.h2d_x, w.h2d_sets, w.out_E,
                   w.out_P, w.out_res, w.polish_jobs, w.polish_partial, w.polish_barrier,
                   w.polish_x, w.polish_E, w.flow_jobs, w.flow_x, w.flow_EP};
   for (void* p : ptrs)
@@ -1232,14 +1332,42 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
         pp_per_tile = std::max(64, std::min(kMaxTilePairs, t));
       }
     }
-    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 3], s_back);
-    plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile);
-    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 4], s_back);
-    if (allow_fast)
-      score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
-                                                              notin, out);
-    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 5], s_back);
     const int X = std::max(1, std::min(4096, (4 * ctx->sm_count + nb - 1) / nb));
+    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 3], s_back);
+    // staging only pays when the scoring work dwarfs the extra launches (~10 small kernels)
+    const bool staged = ctx->early_exit && allow_fast && !two_stage &&
+                        (double)nb * H * 3.0 * (2.0 * cmax_pp) >= 2.0e8;
+    if (staged) {
+      // staged scoring with exact pruning (see set_stage / stage_leader / prune_compact)
+      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 4], s_back);
+      const Hyp32* alt_hyp = w.hyp2 + so * 10;
+      const int32_t* alt_id = w.hyp_id2 + so * 10;
+      const uint32_t* alt_out = w.out2 + so * 10;
+      for (int stg = 0; stg < kEarlyStages; ++stg) {
+        set_stage<<<(nb + 127) / 128, 128, 0, s_back>>>(desc, state, nb, kEarlyFrac[stg], kEarlyFrac[stg + 1], stg == 0,
+                                                        pp_per_tile);
+        plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile);
+        score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
+                                                                notin, out);
+        if (stg + 1 < kEarlyStages) {
+          stage_leader<<<nb, 256, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
+          exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
+          prune_compact<<<nb, 256, 0, s_back>>>(desc, state, H, hyp, hyp_id, out, cand_cnt, (Hyp32*)alt_hyp,
+                                                (int32_t*)alt_id, (uint32_t*)alt_out);
+          std::swap(hyp, alt_hyp);
+          { const int32_t* t = hyp_id; hyp_id = (int32_t*)alt_id; alt_id = t; }
+          { const uint32_t* t = out; out = (uint32_t*)alt_out; alt_out = t; }
+        }
+      }
+      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 5], s_back);
+    } else {
+      plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile);
+      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 4], s_back);
+      if (allow_fast)
+        score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
+                                                                notin, out);
+      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 5], s_back);
+    }
     pick_top<<<nb, 256, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
     if (two_stage) {
       // (single chunk) stage A runs on n_pre points: exact_counts reads n_full, so the descriptors
@@ -1727,6 +1855,12 @@ int tv5_measure_fp32_peak(tv5_ctx* ctx, int mode, double* tflops_out) {
 int tv5_set_force_exact(tv5_ctx* ctx, int on) {
   if (!ctx) return TV5_ERR_INVALID;
   ctx->force_exact = on != 0;
+  return TV5_OK;
+}
+
+int tv5_set_early_exit(tv5_ctx* ctx, int on) {
+  if (!ctx) return TV5_ERR_INVALID;
+  ctx->early_exit = on != 0;
   return TV5_OK;
 }
 

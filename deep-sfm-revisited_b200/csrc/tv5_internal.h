@@ -32,6 +32,8 @@ constexpr int kHostChunks = 8;       // pipeline depth of the host-buffer entry 
 constexpr int kPipeChunks = 8;       // chunks of pairs of one submission (solver / scorer overlap)
 constexpr int kPipeMinPairs = 16;    // ... each at least this many pairs
 constexpr int kProfPerChunk = 8;     // profiling events per chunk
+constexpr int kEarlyStages = 3;      // early exit: scoring stages ...
+constexpr float kEarlyFrac[kEarlyStages + 1] = {0.0f, 0.30f, 0.52f, 1.0f};  // ... as fractions of a pair's points
 
 // Per image pair: geometry of the job (written by the host) ...
 struct PairDesc {
@@ -59,7 +61,8 @@ struct PairState {
   int32_t n_cand;         // hypotheses to re-score exactly (atomic)
   int32_t exact_from;     // first candidate not yet re-scored
   int32_t n_entries;      // isolated real roots of the pair (split solver, atomic)
-  int32_t pad2;
+  int32_t M_total;        // hypotheses produced by the solver (M shrinks when early exit prunes)
+  int32_t pp_lo, pp_hi;   // point pairs [pp_lo, pp_hi) scored by the current stage (pp_hi = 0: all)
   double s_scale;         // sqrt(1-c)/thr folded into the float32 point / hypothesis records
   BandConst band;
 };
@@ -85,6 +88,9 @@ struct Workspace {
   int32_t* hyp_id = nullptr;                          // [B*H*10]  set*16 + root
   uint32_t* notin = nullptr;                          // [B*H*10]
   uint32_t* out = nullptr;                            // [B*H*10]
+  Hyp32* hyp2 = nullptr;                              // [B*H*10]  early exit: survivors (ping-pong)
+  int32_t* hyp_id2 = nullptr;
+  uint32_t* out2 = nullptr;
   int32_t* cand = nullptr;                            // [B*H*10]  hypothesis slots to re-score
   int32_t* cand_cnt = nullptr;                        // [B*H*10]  exact counts of the candidates
   // staging for the host-buffer entry point
@@ -126,6 +132,7 @@ struct tv5_ctx {
   cudaEvent_t start_ev = nullptr;
   int polish_max_ctas = 0;              // co-resident CTAs of irls_polish on this device
   // solver / scorer overlap inside one submission
+  bool early_exit = false;              // staged scoring with exact hypothesis pruning (opt-in)
   bool split_solver = true;             // three-kernel solver (solve5_split.cuh) instead of solve_sets
   bool overlap = false;
   bool profiling_serial = false;

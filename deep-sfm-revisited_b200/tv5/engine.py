@@ -426,6 +426,11 @@ class Engine:
     def set_force_exact(self, on=True):
         _check(self.ctx, self.L.tv5_set_force_exact(self.ctx, int(bool(on))), "set_force_exact")
 
+    def set_early_exit(self, on=True):
+        """Staged scoring with exact hypothesis pruning (default off); results do not depend on it."""
+        _check(self.ctx, self.L.tv5_set_early_exit(self.ctx, int(bool(on))), "set_early_exit")
+        self.early_exit = bool(on)
+
     def set_split_solver(self, on=True):
         """Three-kernel solver (default) vs the fused kernel; results do not depend on it."""
         _check(self.ctx, self.L.tv5_set_split_solver(self.ctx, int(bool(on))), "set_split_solver")

@@ -726,3 +726,39 @@ def test_split_solver_is_bit_identical_to_fused_solver(engine, std_pair):
             assert torch.equal(a[k], b[k]), k          # same arithmetic sequence per root: bit-identical
     assert torch.equal(rf.E, rs.E) and torch.equal(rf.P, rs.P) and torch.equal(rf.mask, rs.mask)
     assert torch.equal(rf.stats[:5], rs.stats[:5])      # count, set, (compacted) root, M, candidates
+
+
+# ---------------------------------------------------------------------------------------------
+# early exit (opt-in): staged scoring with exact hypothesis pruning
+# ---------------------------------------------------------------------------------------------
+def test_early_exit_gives_identical_results(engine, std_pair):
+    """Winner, count, E, P, mask and the hypothesis total are those of the full scoring, on the
+    standard pair, on ragged batches (including pairs too small to stage, a pair without inliers
+    and a float64-path pair), and with the reference's minimal sets."""
+    sc, x1, x2 = std_pair
+    rng = np.random.default_rng(5)
+    ns = [10000, 9999, 777, 5, 2048, 300, 4097, 1500]
+    pairs = [synth.make_pair(n, **{**synth.pair_variation(i), "seed": 400 + i}) for i, n in enumerate(ns)]
+    pairs[5]["x2"] = rng.normal(0, 0.5, pairs[5]["x2"].shape)            # pure outliers
+    pairs[7]["x1"] = pairs[7]["x1"] * 3000.0                              # |x| > 1024: float64 scorer
+    X1 = dev(np.concatenate([p["x1"] for p in pairs])); X2 = dev(np.concatenate([p["x2"] for p in pairs]))
+    off = np.r_[0, np.cumsum(ns)]
+    sets = dev(np.stack([synth.make_sets(n, 2048, 60 + i) for i, n in enumerate(ns)]), torch.int32)
+
+    def run():
+        a = engine.compute_pose(x1, x2, 8, THR, want_mask=True)            # reference RNG table
+        b = engine.compute_pose_batch(X1, X2, off, 4, THR, sets=sets, want_mask=True)
+        return a, b
+
+    full = run()
+    try:
+        engine.set_early_exit(True)
+        fast = run()
+    finally:
+        engine.set_early_exit(False)
+    for f, e in zip(full, fast):
+        assert torch.equal(f.E, e.E) and torch.equal(f.P, e.P) and torch.equal(f.mask, e.mask)
+        sf, se = f.stats.reshape(-1, 8), e.stats.reshape(-1, 8)
+        assert torch.equal(sf[:, :4], se[:, :4])        # count, set, root, total hypotheses
+        assert torch.equal(sf[:, 5], se[:, 5])          # same scorer path per pair
+    assert int(fast[1].fast_path[7]) == 0 and int(fast[1].fast_path[0]) == 1

@@ -8,6 +8,7 @@ from tv5 import synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 eng = tv5.get_engine()
 eng.set_overlap(os.environ.get('TV5_OVERLAP', '0') != '0')
+eng.set_early_exit(os.environ.get('TV5_EARLY', '0') == '1')
 pairs = [synth.make_pair(10000, **synth.pair_variation(i)) for i in range(B)]
 x1 = torch.from_numpy(np.concatenate([p["x1"] for p in pairs])).cuda()
 x2 = torch.from_numpy(np.concatenate([p["x2"] for p in pairs])).cuda()
