@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1343,13 +1344,14 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
       const Hyp32* alt_hyp = w.hyp2 + so * 10;
       const int32_t* alt_id = w.hyp_id2 + so * 10;
       const uint32_t* alt_out = w.out2 + so * 10;
-      for (int stg = 0; stg < kEarlyStages; ++stg) {
-        set_stage<<<(nb + 127) / 128, 128, 0, s_back>>>(desc, state, nb, kEarlyFrac[stg], kEarlyFrac[stg + 1], stg == 0,
+      const int n_stages = ctx->early_stages;
+      for (int stg = 0; stg < n_stages; ++stg) {
+        set_stage<<<(nb + 127) / 128, 128, 0, s_back>>>(desc, state, nb, ctx->early_frac[stg], ctx->early_frac[stg + 1], stg == 0,
                                                         pp_per_tile);
         plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile);
         score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
                                                                 notin, out);
-        if (stg + 1 < kEarlyStages) {
+        if (stg + 1 < n_stages) {
           stage_leader<<<nb, 256, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
           exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
           prune_compact<<<nb, 256, 0, s_back>>>(desc, state, H, hyp, hyp_id, out, cand_cnt, (Hyp32*)alt_hyp,
@@ -1861,6 +1863,22 @@ int tv5_set_force_exact(tv5_ctx* ctx, int on) {
 int tv5_set_early_exit(tv5_ctx* ctx, int on) {
   if (!ctx) return TV5_ERR_INVALID;
   ctx->early_exit = on != 0;
+  // development knob: TV5_EARLY_FRAC="0.3,0.52" = interior stage boundaries
+  if (const char* e = getenv("TV5_EARLY_FRAC")) {
+    int n = 0;
+    float f[kEarlyMaxStages + 1] = {0.0f};
+    const char* p = e;
+    while (*p && n + 1 < kEarlyMaxStages) {
+      char* end = nullptr;
+      const float v = strtof(p, &end);
+      if (end == p) break;
+      if (v > f[n] && v < 1.0f) f[++n] = v;
+      p = (*end == ',') ? end + 1 : end;
+    }
+    f[++n] = 1.0f;
+    ctx->early_stages = n;
+    for (int i = 0; i <= n; ++i) ctx->early_frac[i] = f[i];
+  }
   return TV5_OK;
 }
 

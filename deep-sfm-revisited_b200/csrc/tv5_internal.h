@@ -32,8 +32,7 @@ constexpr int kHostChunks = 8;       // pipeline depth of the host-buffer entry 
 constexpr int kPipeChunks = 8;       // chunks of pairs of one submission (solver / scorer overlap)
 constexpr int kPipeMinPairs = 16;    // ... each at least this many pairs
 constexpr int kProfPerChunk = 8;     // profiling events per chunk
-constexpr int kEarlyStages = 3;      // early exit: scoring stages ...
-constexpr float kEarlyFrac[kEarlyStages + 1] = {0.0f, 0.30f, 0.52f, 1.0f};  // ... as fractions of a pair's points
+constexpr int kEarlyMaxStages = 6;   // early exit: at most this many scoring stages
 
 // Per image pair: geometry of the job (written by the host) ...
 struct PairDesc {
@@ -133,6 +132,8 @@ struct tv5_ctx {
   int polish_max_ctas = 0;              // co-resident CTAs of irls_polish on this device
   // solver / scorer overlap inside one submission
   bool early_exit = false;              // staged scoring with exact hypothesis pruning (opt-in)
+  int early_stages = 3;                 // ... stage boundaries as fractions of a pair's points
+  float early_frac[tv5::kEarlyMaxStages + 1] = {0.0f, 0.30f, 0.52f, 1.0f};
   bool split_solver = true;             // three-kernel solver (solve5_split.cuh) instead of solve_sets
   bool overlap = false;
   bool profiling_serial = false;
