@@ -99,8 +99,9 @@ __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[kC
     // ---- Gauss-Jordan with partial pivoting on columns 0..9, rows spread over the group's lanes
     int pivcol[kCoopJam];
     bool bad[kCoopJam];
+    double pivval[kCoopJam];
 #pragma unroll
-    for (int v = 0; v < kCoopJam; ++v) { pivcol[v] = -1; bad[v] = false; }
+    for (int v = 0; v < kCoopJam; ++v) { pivcol[v] = -1; bad[v] = false; pivval[v] = 1.0; }
 #pragma unroll
     for (int c = 0; c < 10; ++c) {
       // partial pivoting: all-reduce (max is idempotent) over the 10-lane ring by rotations
@@ -120,35 +121,34 @@ __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[kC
           key[v] = other > key[v] ? other : key[v];
         }
       }
+      // The pivot row is NOT normalised while eliminating: with multiplier g = row[c] / pivot (0 on
+      // the pivot lane itself) every lane does  row[j] -= g * pivot_row[j]  — one fma per column and
+      // no select; the surviving rows are divided by their pivot once, at the end.
       int bl[kCoopJam];
-      double inv[kCoopJam], f[kCoopJam];
+      double g[kCoopJam];
 #pragma unroll
       for (int v = 0; v < kCoopJam; ++v) {
         bl[v] = (key[v] >> 5) ? (int)(key[v] & 31u) : gb;
         const float best = __uint_as_float(key[v] & ~31u);
         bad[v] = bad[v] || !(best > 0.f) || !(best < 3.0e38f);
-        inv[v] = __drcp_rn(__shfl_sync(FULL, row[v][c], bl[v]));
-        f[v] = row[v][c];
+        const double piv = __shfl_sync(FULL, row[v][c], bl[v]);
+        g[v] = (lane == bl[v]) ? 0.0 : -(row[v][c] * __drcp_rn(piv));
+        if (lane == bl[v]) { pivcol[v] = c; pivval[v] = piv; }
       }
 #pragma unroll
       for (int j = c + 1; j < 20; ++j) {
 #pragma unroll
-        for (int v = 0; v < kCoopJam; ++v) {
-          const double pj = __shfl_sync(FULL, row[v][j], bl[v]) * inv[v];
-          row[v][j] = (lane == bl[v]) ? pj : fma(-f[v], pj, row[v][j]);
-        }
+        for (int v = 0; v < kCoopJam; ++v) row[v][j] = fma(g[v], __shfl_sync(FULL, row[v][j], bl[v]), row[v][j]);
       }
-#pragma unroll
-      for (int v = 0; v < kCoopJam; ++v)
-        if (lane == bl[v]) pivcol[v] = c;
     }
 #pragma unroll
     for (int v = 0; v < kCoopJam; ++v) {
       const unsigned badmask = __ballot_sync(FULL, bad[v] && rowlane);
       if (active[v]) {
         if (pivcol[v] >= 4) {
+          const double sc = __drcp_rn(pivval[v]);
 #pragma unroll
-          for (int j = 0; j < 10; ++j) sR[(pivcol[v] - 4) * 10 + j][sw[v]] = row[v][10 + j];
+          for (int j = 0; j < 10; ++j) sR[(pivcol[v] - 4) * 10 + j][sw[v]] = row[v][10 + j] * sc;
         }
         if (r == 0) sOk[sw[v]] = ((badmask >> gb) & 0x3ffu) ? 0 : 1;
       }
