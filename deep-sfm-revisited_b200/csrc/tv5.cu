@@ -537,7 +537,7 @@ __global__ void set_stage(const PairDesc* __restrict__ desc, PairState* __restri
   if (first) state[b].M_total = state[b].M;
 }
 
-__global__ void __launch_bounds__(256) stage_leader(const PairDesc* __restrict__ desc,
+__global__ void __launch_bounds__(1024) stage_leader(const PairDesc* __restrict__ desc,
                                                     PairState* __restrict__ state, int H,
                                                     const uint32_t* __restrict__ out,
                                                     const int32_t* __restrict__ hyp_id,
@@ -551,8 +551,9 @@ __global__ void __launch_bounds__(256) stage_leader(const PairDesc* __restrict__
     if (threadIdx.x == 0) s.n_cand = 0;
     return;
   }
-  __shared__ unsigned long long s_key[8];
+  __shared__ unsigned long long s_key[32];
   unsigned long long key = 0ull;  // (fewest sure outliers, smallest id) as a maximum
+#pragma unroll 4
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
     const unsigned long long k = ((unsigned long long)(0xFFFFFFFFu - out[base + m]) << 32) |
                                  (0xFFFFFFFFu - (uint32_t)hyp_id[base + m]);
@@ -562,8 +563,7 @@ __global__ void __launch_bounds__(256) stage_leader(const PairDesc* __restrict__
   if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
   __syncthreads();
   unsigned long long best = 0ull;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) best = s_key[w] > best ? s_key[w] : best;
+for (int w = 0; w < (int)(blockDim.x >> 5); ++w) best = s_key[w] > best ? s_key[w] : best;
   const int best_id = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
   if (threadIdx.x == 0) s.n_cand = 1;
   for (int m = threadIdx.x; m < M; m += blockDim.x)
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(256) prune_compact(const PairDesc* __restrict_
 // The true winner w has exact(w) >= L and hi(w) >= exact(w), so it is in the second set; ties
 // are all included, so the first-maximum rule can be applied exactly by `finalize`.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pick_top(const PairDesc* __restrict__ desc,
+__global__ void __launch_bounds__(1024) pick_top(const PairDesc* __restrict__ desc,
                                                 PairState* __restrict__ state, int H,
                                                 const uint32_t* __restrict__ out,
                                                 const int32_t* __restrict__ hyp_id,
@@ -630,9 +630,10 @@ __global__ void __launch_bounds__(256) pick_top(const PairDesc* __restrict__ des
     if (threadIdx.x == 0) { s.n_cand = M; s.exact_from = 0; }
     return;
   }
-  __shared__ unsigned long long s_key[8];
+  __shared__ unsigned long long s_key[32];
   const int n = desc[b].n_full;
   unsigned long long key = 0ull;  // (hi << 32 | ~id) << 0, slot recovered by a second pass
+#pragma unroll 4
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
     const uint32_t hi = (uint32_t)(n - (int)out[base + m]);
     const unsigned long long k = ((unsigned long long)hi << 32) | (0xFFFFFFFFu - (uint32_t)hyp_id[base + m]);
@@ -642,15 +643,14 @@ __global__ void __launch_bounds__(256) pick_top(const PairDesc* __restrict__ des
   if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
   __syncthreads();
   unsigned long long best = 0ull;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) best = s_key[w] > best ? s_key[w] : best;
+for (int w = 0; w < (int)(blockDim.x >> 5); ++w) best = s_key[w] > best ? s_key[w] : best;
   const int best_id = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
   if (threadIdx.x == 0) { s.n_cand = M > 0 ? 1 : 0; s.exact_from = 0; }
   for (int m = threadIdx.x; m < M; m += blockDim.x)
     if (hyp_id[base + m] == best_id) { cand[base] = m; cand_cnt[base] = 0; }
 }
 
-__global__ void __launch_bounds__(256) pick_rest(const PairDesc* __restrict__ desc,
+__global__ void __launch_bounds__(1024) pick_rest(const PairDesc* __restrict__ desc,
                                                  PairState* __restrict__ state, int H,
                                                  const uint32_t* __restrict__ out,
                                                  int32_t* __restrict__ cand,
@@ -1352,7 +1352,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
         score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
                                                                 notin, out);
         if (stg + 1 < n_stages) {
-          stage_leader<<<nb, 256, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
+          stage_leader<<<nb, 1024, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
           exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
           prune_compact<<<nb, 256, 0, s_back>>>(desc, state, H, hyp, hyp_id, out, cand_cnt, (Hyp32*)alt_hyp,
                                                 (int32_t*)alt_id, (uint32_t*)alt_out);
@@ -1370,7 +1370,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
                                                                 notin, out);
       if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 5], s_back);
     }
-    pick_top<<<nb, 256, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
+    pick_top<<<nb, 1024, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
     if (two_stage) {
       // (single chunk) stage A runs on n_pre points: exact_counts reads n_full, so the descriptors
       // are re-uploaded with n_full := n_pre for this stage and restored afterwards.
@@ -1384,7 +1384,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
     } else {
       exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
       if (allow_fast) {
-        pick_rest<<<nb, 256, 0, s_back>>>(desc, state, H, out, cand, cand_cnt);
+        pick_rest<<<nb, 1024, 0, s_back>>>(desc, state, H, out, cand, cand_cnt);
         exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
       }
     }
