@@ -1195,6 +1195,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
                            const cudaEvent_t* ready_ev, const int* ready_first, int n_ready) {
   if (!ctx || B < 1 || !x1 || !x2 || !pt_offsets || iters < 1 || !E_out || !result) return TV5_ERR_INVALID;
   if (!(thr > 0.0) || !(thr < 1e300)) return TV5_ERR_INVALID;
+  if (B > 65535 || iters > (1 << 20) / TV5_REF_THREADS) return TV5_ERR_INVALID;   // grid.y / index ranges
   cudaStream_t st = (cudaStream_t)stream;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
   profile_collect(ctx);
