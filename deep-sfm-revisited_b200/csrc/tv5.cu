@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(1024) plan_tiles(const PairDesc* __restrict__ 
     if (b < B) {
       PairState& s = state[b];
       const int npp_all = (desc[b].n_full + 1) >> 1;
-      if (s.pp_hi <= 0) { s.pp_lo = 0; s.pp_hi = npp_all; }   // no staging: the whole pair
+      if (!s.staged) { s.pp_lo = 0; s.pp_hi = npp_all; }      // no staging: the whole pair
       const int npp = max(0, min(s.pp_hi, npp_all) - s.pp_lo);
       s.n_hc = (s.M + kHypChunk - 1) / kHypChunk;
       s.n_pc = (npp + pp_per_tile - 1) / pp_per_tile;
@@ -534,6 +534,7 @@ __global__ void set_stage(const PairDesc* __restrict__ desc, PairState* __restri
   const int hi = f_hi >= 1.f ? npp : min(npp, (((int)(f_hi * npp) + q / 2) / q) * q);
   state[b].pp_lo = lo;
   state[b].pp_hi = max(hi, lo);
+  state[b].staged = 1;
   if (first) state[b].M_total = state[b].M;
 }
 

@@ -61,7 +61,9 @@ struct PairState {
   int32_t exact_from;     // first candidate not yet re-scored
   int32_t n_entries;      // isolated real roots of the pair (split solver, atomic)
   int32_t M_total;        // hypotheses produced by the solver (M shrinks when early exit prunes)
-  int32_t pp_lo, pp_hi;   // point pairs [pp_lo, pp_hi) scored by the current stage (pp_hi = 0: all)
+  int32_t pp_lo, pp_hi;   // point pairs [pp_lo, pp_hi) scored by the current stage ...
+  int32_t staged;         // ... when != 0; otherwise the whole pair
+  int32_t pad2;
   double s_scale;         // sqrt(1-c)/thr folded into the float32 point / hypothesis records
   BandConst band;
 };

@@ -737,7 +737,7 @@ def test_early_exit_gives_identical_results(engine, std_pair):
     and a float64-path pair), and with the reference's minimal sets."""
     sc, x1, x2 = std_pair
     rng = np.random.default_rng(5)
-    ns = [10000, 9999, 777, 5, 2048, 300, 4097, 1500]
+    ns = [10000, 9999, 777, 5, 2048, 300, 4097, 1500, 17, 64, 130, 257]   # small ones: stages collapse
     pairs = [synth.make_pair(n, **{**synth.pair_variation(i), "seed": 400 + i}) for i, n in enumerate(ns)]
     pairs[5]["x2"] = rng.normal(0, 0.5, pairs[5]["x2"].shape)            # pure outliers
     pairs[7]["x1"] = pairs[7]["x1"] * 3000.0                              # |x| > 1024: float64 scorer
