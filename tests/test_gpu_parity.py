@@ -762,3 +762,22 @@ def test_early_exit_gives_identical_results(engine, std_pair):
         assert torch.equal(sf[:, :4], se[:, :4])        # count, set, root, total hypotheses
         assert torch.equal(sf[:, 5], se[:, 5])          # same scorer path per pair
     assert int(fast[1].fast_path[7]) == 0 and int(fast[1].fast_path[0]) == 1
+
+
+@pytest.mark.parametrize("outlier_frac,noise_px", [(0.0, 0.0), (0.5, 0.05), (0.85, 0.3), (1.0, 0.05)])
+def test_early_exit_identical_across_inlier_regimes(engine, outlier_frac, noise_px):
+    """Exactness of the pruning does not depend on how many inliers there are: noise-free (every
+    all-inlier set ties at count N), half outliers, mostly outliers with heavy noise, no structure."""
+    B, n = 8, 6000
+    pairs = [synth.make_pair(n, seed=700 + i, outlier_frac=outlier_frac, noise_px=noise_px) for i in range(B)]
+    X1 = dev(np.concatenate([p["x1"] for p in pairs])); X2 = dev(np.concatenate([p["x2"] for p in pairs]))
+    off = np.arange(B + 1) * n
+    sets = dev(np.stack([synth.make_sets(n, 4096, 800 + i) for i in range(B)]), torch.int32)
+    full = engine.compute_pose_batch(X1, X2, off, 8, THR, sets=sets, want_mask=True)
+    try:
+        engine.set_early_exit(True)
+        fast = engine.compute_pose_batch(X1, X2, off, 8, THR, sets=sets, want_mask=True)
+    finally:
+        engine.set_early_exit(False)
+    assert torch.equal(full.E, fast.E) and torch.equal(full.P, fast.P) and torch.equal(full.mask, fast.mask)
+    assert torch.equal(full.stats[:, :4], fast.stats[:, :4])
