@@ -368,7 +368,8 @@ __global__ void hyps_from_list(const double* __restrict__ E_list, int M, PairSta
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) plan_tiles(const PairDesc* __restrict__ desc,
                                                    PairState* __restrict__ state,
-                                                   Control* __restrict__ ctl, int B, int pp_per_tile) {
+                                                   Control* __restrict__ ctl, int B, int pp_per_tile,
+                                                   int hyp_chunk) {
   __shared__ int s_warp[32];
   __shared__ int s_base;
   if (threadIdx.x == 0) s_base = 0;
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(1024) plan_tiles(const PairDesc* __restrict__ 
       const int npp_all = (desc[b].n_full + 1) >> 1;
       if (!s.staged) { s.pp_lo = 0; s.pp_hi = npp_all; }      // no staging: the whole pair
       const int npp = max(0, min(s.pp_hi, npp_all) - s.pp_lo);
-      s.n_hc = (s.M + kHypChunk - 1) / kHypChunk;
+      s.n_hc = (s.M + hyp_chunk - 1) / hyp_chunk;
       s.n_pc = (npp + pp_per_tile - 1) / pp_per_tile;
       tiles = s.fast ? s.n_hc * s.n_pc : 0;
     }
@@ -420,8 +421,10 @@ __global__ void __launch_bounds__(1024) plan_tiles(const PairDesc* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // score_bounds: persistent CTAs pulling (pair, hypothesis chunk, point chunk) tiles.
 // ------------------------------------------------------------------------------------------
-template <bool TWO_SIDED>
-__global__ void __launch_bounds__(kScoreThreads, TV5_SCORE_MINB)
+// HPT hypotheses per thread: kHypPerThread for the bulk of the work; 1 (256-slot chunks, more CTAs
+// per SM) for the late early-exit stages, where a pair has only a few hundred hypotheses left.
+template <bool TWO_SIDED, int HPT = kHypPerThread>
+__global__ void __launch_bounds__(kScoreThreads, (HPT >= kHypPerThread ? TV5_SCORE_MINB : 4))
 score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ state,
              Control* __restrict__ ctl, int B, int H, int pp_per_tile,
              const PointPair32* __restrict__ pp, const Hyp32* __restrict__ hyp,
@@ -460,12 +463,12 @@ score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ st
       bulk_load(tile, pp + d.pp_off + pp0, bytes, &bar);
     }
     // hypotheses of this thread (registers), loaded while the bulk copy is in flight
-    const size_t hbase = (size_t)b * H * 10 + (size_t)hc * kHypChunk;
-    HypRegs hr[kHypPerThread];
-    bool live[kHypPerThread];
+    const size_t hbase = (size_t)b * H * 10 + (size_t)hc * (kScoreThreads * HPT);
+    HypRegs hr[HPT];
+    bool live[HPT];
 #pragma unroll
-    for (int k = 0; k < kHypPerThread; ++k) {
-      const int m = hc * kHypChunk + k * kScoreThreads + tid;
+    for (int k = 0; k < HPT; ++k) {
+      const int m = hc * (kScoreThreads * HPT) + k * kScoreThreads + tid;
       live[k] = m < s.M;
       Hyp32 raw;
       if (live[k]) {
@@ -480,9 +483,9 @@ score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ st
       load_hyp(hr[k], raw);
     }
     const float2 bK = dup(s.band.K), nratio = dup(-s.band.ratio), ntwoK = dup(-s.band.two_K);
-    uint32_t a[kHypPerThread], o[kHypPerThread];
+    uint32_t a[HPT], o[HPT];
 #pragma unroll
-    for (int k = 0; k < kHypPerThread; ++k) { a[k] = 0u; o[k] = 0u; }
+    for (int k = 0; k < HPT; ++k) { a[k] = 0u; o[k] = 0u; }
 
     mbar_wait(&bar, phase);
     phase ^= 1u;
@@ -493,16 +496,16 @@ score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ st
     for (int i = 0; i < nfull; ++i) {
       const PointPair32 p = tile[i];
 #pragma unroll
-      for (int k = 0; k < kHypPerThread; ++k) eval_pair<TWO_SIDED>(hr[k], p, bK, nratio, ntwoK, a[k], o[k]);
+      for (int k = 0; k < HPT; ++k) eval_pair<TWO_SIDED>(hr[k], p, bK, nratio, ntwoK, a[k], o[k]);
     }
     if (odd_tail) {
       const PointPair32 p = tile[nfull];
 #pragma unroll
-      for (int k = 0; k < kHypPerThread; ++k)
+      for (int k = 0; k < HPT; ++k)
         eval_pair<TWO_SIDED>(hr[k], p, bK, nratio, ntwoK, a[k], o[k], false);
     }
 #pragma unroll
-    for (int k = 0; k < kHypPerThread; ++k)
+    for (int k = 0; k < HPT; ++k)
       if (live[k]) {
         const size_t slot = hbase + k * kScoreThreads + tid;
         if (TWO_SIDED && a[k]) atomicAdd(&notin[slot], a[k]);
@@ -1350,9 +1353,15 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
       for (int stg = 0; stg < n_stages; ++stg) {
         set_stage<<<(nb + 127) / 128, 128, 0, s_back>>>(desc, state, nb, ctx->early_frac[stg], ctx->early_frac[stg + 1], stg == 0,
                                                         pp_per_tile);
-        plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile);
-        score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
-                                                                notin, out);
+        if (stg == 0) {
+          plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile, kHypChunk);
+          score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
+                                                                  notin, out);
+        } else {  // few survivors per pair: 256-slot hypothesis chunks
+          plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile, kScoreThreads);
+          score_bounds<false, 1><<<4 * ctx->sm_count, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile,
+                                                                                 w.pp, hyp, notin, out);
+        }
         if (stg + 1 < n_stages) {
           stage_leader<<<nb, 1024, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
           exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
@@ -1365,7 +1374,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
       }
       if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 5], s_back);
     } else {
-      plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile);
+      plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile, kHypChunk);
       if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 4], s_back);
       if (allow_fast)
         score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
@@ -1586,7 +1595,7 @@ int tv5_score_bounds(tv5_ctx* ctx, void* stream, const double* x1, const double*
       pp_per_tile = std::max(64, std::min(kMaxTilePairs, t));
     }
   }
-  plan_tiles<<<1, 1024, 0, st>>>(w.desc, w.state, w.ctl, 1, pp_per_tile);
+  plan_tiles<<<1, 1024, 0, st>>>(w.desc, w.state, w.ctl, 1, pp_per_tile, kHypChunk);
   stage_mark(ctx, st, 3);
   // H*10 is the stride between pairs inside the kernel; with one pair it is irrelevant
   score_bounds<true><<<slots, kScoreThreads, 0, st>>>(w.desc, w.state, w.ctl, 1, H, pp_per_tile, w.pp, w.hyp,
