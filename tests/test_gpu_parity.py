@@ -781,3 +781,50 @@ def test_early_exit_identical_across_inlier_regimes(engine, outlier_frac, noise_
         engine.set_early_exit(False)
     assert torch.equal(full.E, fast.E) and torch.equal(full.P, fast.P) and torch.equal(full.mask, fast.mask)
     assert torch.equal(full.stats[:, :4], fast.stats[:, :4])
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 5, 7, 3), (2, 3, 9, 33, 5), (1, 2, 2, 2, 1), (1, 5, 17, 31, 33)])
+def test_plane_sweep_odd_shapes(engine, shape):
+    """Shapes that exercise the per-plane store shift (h*w odd, nlabel not a multiple of 32), one
+    channel, the smallest image grid_sample accepts."""
+    import ref_planesweep_torch as rp
+    from test_oracle import sweep_tolerance
+    B, C, h, w, L = shape
+    rng = np.random.default_rng(sum(shape))
+    ref = rng.normal(0, 1, (B, C, h, w)).astype(np.float32)
+    tgt = rng.normal(0, 1, (B, C, h, w)).astype(np.float32)
+    K = np.array([[0.9 * w, 0, 0.5 * w], [0, 0.9 * w, 0.5 * h], [0, 0, 1.0]])
+    K4 = np.stack([K] * B).astype(np.float32); Kinv4 = np.stack([np.linalg.inv(K)] * B).astype(np.float32)
+    R = synth.rodrigues((0.01, -0.02, 0.005)); t = np.array([0.1, -0.05, -0.3])
+    pose = np.stack([np.concatenate([R, t[:, None]], 1)] * B).astype(np.float32)
+    dv = [dev(a, torch.float32) for a in (ref, tgt, pose, K4, Kinv4)]
+    mine = engine.plane_sweep(*dv, L, 1.0).cpu().numpy()
+    ct = rp.cost_volume(*dv, L, 1.0).cpu().numpy()
+    assert mine.shape == (B, 2 * C, L, h, w)
+    assert (mine[:, :C] == ct[:, :C]).all()
+    for b in range(B):
+        co = oracle.plane_sweep_cost_volume(ref[b], tgt[b], pose[b], K4[b], Kinv4[b], L, 1.0)
+        assert np.abs(mine[b, C:] - co[C:]).max() <= sweep_tolerance(h, w, tgt)
+    # against torch: the same bound wherever the projection is well conditioned (Z >= 1: depth >= 1.3)
+    far = [i for i in range(L) if 1.0 * L / (i + 1) >= 1.3]
+    if far:
+        assert np.abs(mine[:, C:, far] - ct[:, C:, far]).max() <= 4 * sweep_tolerance(h, w, tgt)
+
+
+def test_flow_to_points_small_images_and_zero_margin(engine):
+    rng = np.random.default_rng(2)
+    for (H, W, margin) in ((3, 4, 0), (8, 8, 3), (21, 5, 2)):
+        flow = rng.normal(0, 1, (2, 2, H, W)).astype(np.float32)
+        Kinv = np.stack([np.linalg.inv(synth.KITTI_K)] * 2).astype(np.float32)
+        x1, x2, off = engine.flow_to_points(dev(flow, torch.float32), dev(Kinv, torch.float32), margin)
+        assert off[-1] == 2 * (H - 2 * margin) * (W - 2 * margin)
+        for b in range(2):
+            oa, oc = oracle.flow_to_points(flow[b], Kinv[b], margin) if margin else _flow_margin0(flow[b], Kinv[b])
+            assert (x1[off[b]:off[b + 1]].cpu().numpy() == oa).all() and (x2[off[b]:off[b + 1]].cpu().numpy() == oc).all()
+
+
+def _flow_margin0(flow, Kinv):
+    """oracle with margin 0 (numpy's [0:-0] slice is empty, so go through the gather form)."""
+    _, H, W = flow.shape
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    return oracle.flow_to_points(flow, Kinv, 0, np.stack([xs.reshape(-1), ys.reshape(-1)], 1))
