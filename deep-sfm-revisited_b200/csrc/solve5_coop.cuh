@@ -14,6 +14,11 @@
 
 namespace tv5 {
 
+// 1 = pivot row broadcast through shared memory with 128-bit accesses instead of shuffles: half the
+// LSU wavefronts, but the store -> sync -> load latency per pivot costs more (solve 3.32 -> 3.43 ms)
+#ifndef TV5_COOP_SMEM_BROADCAST
+#define TV5_COOP_SMEM_BROADCAST 0
+#endif
 constexpr int kCoopBasisDoubles = 36;
 constexpr int kCoopRowsDoubles = 60;
 constexpr int kCoopJam = 1;      // rounds carried through the elimination together (2 measured slower: spills)
@@ -77,6 +82,9 @@ __device__ __forceinline__ void coop_build_row(const double (*sB)[kCoopStride], 
 __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[kCoopStride], double (*sR)[kCoopStride],
                                                            int* sOk, int lane) {
   const unsigned FULL = 0xffffffffu;
+#if TV5_COOP_SMEM_BROADCAST
+  __shared__ __align__(16) double sP[3][22];           // pivot row of each group (stride 22: distinct banks)
+#endif
   const int g = lane < 30 ? lane / 10 : 2;            // lanes 30, 31 shadow group 2's shuffles
   const int r = lane < 30 ? lane - 10 * g : lane - 20;  // rows 10, 11 do not take part
   const int gb = 10 * g;
@@ -125,21 +133,40 @@ __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[kC
       // the pivot lane itself) every lane does  row[j] -= g * pivot_row[j]  — one fma per column and
       // no select; the surviving rows are divided by their pivot once, at the end.
       int bl[kCoopJam];
-      double g[kCoopJam];
+      double g_mul[kCoopJam];
 #pragma unroll
       for (int v = 0; v < kCoopJam; ++v) {
         bl[v] = (key[v] >> 5) ? (int)(key[v] & 31u) : gb;
         const float best = __uint_as_float(key[v] & ~31u);
         bad[v] = bad[v] || !(best > 0.f) || !(best < 3.0e38f);
         const double piv = __shfl_sync(FULL, row[v][c], bl[v]);
-        g[v] = (lane == bl[v]) ? 0.0 : -(row[v][c] * __drcp_rn(piv));
+        g_mul[v] = (lane == bl[v]) ? 0.0 : -(row[v][c] * __drcp_rn(piv));
         if (lane == bl[v]) { pivcol[v] = c; pivval[v] = piv; }
       }
+#if TV5_COOP_SMEM_BROADCAST
+      // pivot row to the group through shared memory, two columns per 128-bit access (half the LSU
+      // wavefronts of two 32-bit shuffles per column)
+      static_assert(kCoopJam == 1, "shared-memory broadcast is written for one round in flight");
+      if (lane == bl[0]) {
+#pragma unroll
+        for (int j2 = (c + 1) & ~1; j2 < 20; j2 += 2)
+          *reinterpret_cast<double2*>(&sP[g][j2]) = make_double2(row[0][j2], row[0][j2 + 1]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j2 = (c + 1) & ~1; j2 < 20; j2 += 2) {
+        const double2 pv = *reinterpret_cast<const double2*>(&sP[g][j2]);
+        if (j2 > c) row[0][j2] = fma(g_mul[0], pv.x, row[0][j2]);
+        row[0][j2 + 1] = fma(g_mul[0], pv.y, row[0][j2 + 1]);
+      }
+      __syncwarp();
+#else
 #pragma unroll
       for (int j = c + 1; j < 20; ++j) {
 #pragma unroll
-        for (int v = 0; v < kCoopJam; ++v) row[v][j] = fma(g[v], __shfl_sync(FULL, row[v][j], bl[v]), row[v][j]);
+        for (int v = 0; v < kCoopJam; ++v) row[v][j] = fma(g_mul[v], __shfl_sync(FULL, row[v][j], bl[v]), row[v][j]);
       }
+#endif
     }
 #pragma unroll
     for (int v = 0; v < kCoopJam; ++v) {
