@@ -9,6 +9,11 @@
  * Every function cites the reference lines it follows ("ref:" = path relative to
  * /root/reference/RANSAC_FiveP/essential_matrix/).  Nothing here is used by the product path.
  *
+ * Parity status: PINNED — against the reference's own sources compiled for the host and for the GPU
+ * (oracle/_ref/, build_ref.sh), against fixtures generated from them (tests/golden/*.npz) and, for the
+ * polish functions, against the reference extension imported in the build container (DESIGN.md
+ * section 6; tests/test_oracle.py).
+ *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared tv5_oracle.c -o libtv5_oracle.so -lm
  * (-ffp-contract=off: the only fused operations are the explicit fma() calls in
  * tv5o_sampson_err, which reproduce the contraction nvcc applies to the reference kernel.)
