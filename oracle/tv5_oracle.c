@@ -10,7 +10,7 @@
  * /root/reference/RANSAC_FiveP/essential_matrix/).  Nothing here is used by the product path.
  *
  * Parity status: PINNED — against the reference's own sources compiled for the host and for the GPU
- * (oracle/_ref/, build_ref.sh), against fixtures generated from them (tests/golden/*.npz) and, for the
+ * (oracle/_ref/, build_ref.sh), against fixtures generated from them (the .npz files under tests/golden) and, for the
  * polish functions, against the reference extension imported in the build container (DESIGN.md
  * section 6; tests/test_oracle.py).
  *
@@ -427,6 +427,7 @@ static void isolate(int np, const spoly* s, double lo, double hi, int atlo, int 
 /* ref: sturm.cu:557-676 (find_real_roots_sturm) */
 int tv5o_real_roots(const double* p, int degree, double* roots) {
   spoly s[MAXORD + 2];
+  memset(&s[0], 0, sizeof(s[0]));
   double norm = 1.0 / p[degree];
   for (int i = 0; i <= degree; ++i) s[0].coef[i] = p[i] * norm;
   double val0 = fabs(s[0].coef[0]), fac = 1.0;
