@@ -828,3 +828,57 @@ def _flow_margin0(flow, Kinv):
     _, H, W = flow.shape
     ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
     return oracle.flow_to_points(flow, Kinv, 0, np.stack([xs.reshape(-1), ys.reshape(-1)], 1))
+
+
+# ---------------------------------------------------------------------------------------------
+# the geometric chain of SFMnet's eval forward in miniature (configs[4] without the networks):
+# flow -> correspondences -> pose -> plane sweep -> depth.  Checks that P = [R|t] "from ref to
+# target" is exactly what the plane-sweep warp expects (SURVEY 8(a) conventions).
+# ---------------------------------------------------------------------------------------------
+def test_flow_pose_sweep_chain_recovers_scene_depth(engine):
+    H, W = 96, 160
+    K = np.array([[140.0, 0, 80.0], [0, 140.0, 48.0], [0, 0, 1.0]])
+    Kinv = np.linalg.inv(K)
+    R = synth.rodrigues((0.01, -0.03, 0.005))
+    t = np.array([0.9, 0.1, -0.42]); t /= np.linalg.norm(t)          # unit baseline: depth scale fixed
+    # scene: a valley of two planes n.X = d (camera-1 coordinates), the solid being everything beyond
+    # either plane, so from any camera in the free space the visible depth along a ray is the SMALLER
+    # of the two plane depths (a single plane would leave the classical two-fold planar ambiguity)
+    planes = [(np.array([0.40, 0.05, 1.0]), 12.0), (np.array([-0.45, -0.10, 1.0]), 12.0)]
+    planes = [(n / np.linalg.norm(n), d / np.linalg.norm(n)) for n, d in planes]
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+    pix = np.stack([xs, ys, np.ones_like(xs)], 0).reshape(3, -1)
+    ray = Kinv @ pix
+    D1 = np.min([d / (n @ ray) for n, d in planes], axis=0)           # visible depth in camera 1
+    X1 = ray * D1
+    X2 = R @ X1 + t[:, None]
+    p2 = K @ (X2 / X2[2:3])
+    flow = np.stack([(p2[0] - xs.reshape(-1)).reshape(H, W), (p2[1] - ys.reshape(-1)).reshape(H, W)]).astype(np.float32)
+
+    def texture(X):                                                   # smooth function of the 3-D point, 4 channels
+        f = np.array([[0.9, 0.3, 0.2], [-0.4, 1.1, 0.1], [0.6, -0.7, 0.3], [1.3, 0.5, -0.2]])
+        return np.sin(f @ X * 1.7 + np.arange(4)[:, None])
+
+    planes2 = [(R @ n, d + (R @ n) @ t) for n, d in planes]          # the same planes in camera-2 coordinates
+    D2 = np.min([d / (n @ ray) for n, d in planes2], axis=0)
+    X_of_2 = R.T @ (ray * D2 - t[:, None])                            # camera-1 point seen by each pixel of image 2
+    ref_fea = texture(X1).reshape(1, 4, H, W).astype(np.float32)
+    tgt_fea = texture(X_of_2).reshape(1, 4, H, W).astype(np.float32)
+
+    tf = dev(flow[None], torch.float32); tK = dev(K[None], torch.float32); tKi = dev(Kinv[None], torch.float32)
+    P32, E32, r = engine.pose_from_flow(tf, tKi, 4, THR, margin=4)
+    Pn = r.P[0].cpu().numpy()
+    assert synth.rotation_error_deg(Pn[:, :3], R) < 0.05 and synth.translation_error_deg(Pn[:, 3], t) < 0.5
+    L = 64
+    cost = engine.plane_sweep(dev(ref_fea, torch.float32), dev(tgt_fea, torch.float32), P32, tK, tKi, L, 1.0)
+    diff = (cost[0, :4] - cost[0, 4:]).abs().sum(0)                  # [L, H, W] photometric cost per plane
+    valid = (cost[0, 4:].abs().sum(0) > 0)                            # planes whose warp lands inside the image
+    diff = torch.where(valid, diff, torch.full_like(diff, 1e9))
+    best = diff.argmin(0).cpu().numpy()                               # winning plane per pixel
+    depth = 1.0 * L / (best + 1.0)
+    gt = D1.reshape(H, W)
+    inner = (slice(8, H - 8), slice(8, W - 8))
+    # plane i sits at depth L/(i+1): the quantisation step around depth z is z^2/L
+    step = gt[inner] ** 2 / L
+    err = np.abs(depth[inner] - gt[inner])
+    assert np.median(err / step) < 0.6 and (err < 1.5 * step).mean() > 0.9
