@@ -80,7 +80,7 @@ __device__ __forceinline__ void coop_build_row(const double (*sB)[kCoopStride], 
 // sR[e][lane]: e = r*10 + j, r = 0..5 <-> pivot columns 4..9, j <-> matrix columns 10..19
 // kCoopJam rounds (x 3 sets) are carried through the elimination together.
 __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[kCoopStride], double (*sR)[kCoopStride],
-                                                           int* sOk, int lane) {
+                                                           int* sOk, int lane, int n_sets = 32) {
   const unsigned FULL = 0xffffffffu;
 #if TV5_COOP_SMEM_BROADCAST
   __shared__ __align__(16) double sP[3][22];           // pivot row of each group (stride 22: distinct banks)
@@ -93,7 +93,8 @@ __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[kC
   const int ri = isdet ? 0 : (r - 1) / 3;
   const int rj = isdet ? 0 : (r - 1) - 3 * ri;
 
-  for (int round2 = 0; round2 < (11 + kCoopJam - 1) / kCoopJam; ++round2) {
+  const int n_rounds = (n_sets + 2) / 3;   // three sets per round
+  for (int round2 = 0; round2 < (n_rounds + kCoopJam - 1) / kCoopJam; ++round2) {
     int sw[kCoopJam];
     bool active[kCoopJam];
     double row[kCoopJam][20];

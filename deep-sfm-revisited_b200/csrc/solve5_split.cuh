@@ -36,10 +36,13 @@ struct RootEntry {                  // one isolated real root
 };
 
 // ---- solve_front: grid (ceil(H/32), B), block 32 --------------------------------------------
+// sets_per_warp (32, 16 or 8): lanes >= sets_per_warp idle in the per-set phases and the elimination
+// runs ceil(sets_per_warp / 3) rounds — fewer sets per warp shorten the critical path of small
+// submissions (one 4096-set pair: 128 warps x 11 rounds -> 512 warps x 3 rounds).
 template <typename Gather>
 __device__ __forceinline__ void solve_front_warp(bool valid, const Gather& gather, double* __restrict__ rec_warp,
                                                  int n_sets_here, double (*sB)[kCoopStride],
-                                                 double (*sR)[kCoopStride], int* sOk) {
+                                                 double (*sR)[kCoopStride], int* sOk, int sets_per_warp = 32) {
   const int lane = threadIdx.x & 31;
   bool ok = valid;
   {
@@ -54,9 +57,9 @@ __device__ __forceinline__ void solve_front_warp(bool valid, const Gather& gathe
       for (int c = 0; c < 9; ++c) sB[k * 9 + c][lane] = ok ? B[k][c] : (k == 3 ? 1.0 : 0.0);
   }
   __syncwarp();
-  coop_constraints_eliminate(sB, sR, sOk, lane);
+  coop_constraints_eliminate(sB, sR, sOk, lane, sets_per_warp);
   __syncwarp();
-  ok = ok && sOk[lane];
+  ok = ok && (lane < sets_per_warp) && sOk[lane];
   {
     double Bp[3][3][5], poly[11];
     hidden_matrix_from_rows(sR, lane, Bp);

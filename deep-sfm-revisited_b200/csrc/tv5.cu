@@ -258,18 +258,18 @@ __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ de
 // split solver (solve5_split.cuh): solve_front -> solve_roots -> solve_poses
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) solve_front(const PairDesc* __restrict__ desc, int H,
-                                                  double* __restrict__ rec) {
+                                                  double* __restrict__ rec, int spw) {
   __shared__ double sB[kCoopBasisDoubles][kCoopStride];
   __shared__ double sR[kCoopRowsDoubles][kCoopStride];
   __shared__ int sOk[32];
-  const int h_raw = blockIdx.x * 32 + threadIdx.x;
-  const bool valid = h_raw < H;
-  const int h = valid ? h_raw : H - 1;
+  const int first = blockIdx.x * spw;                 // spw = sets per warp (32, 16 or 8)
+  const int h_raw = first + threadIdx.x;
+  const bool valid = (int)threadIdx.x < spw && h_raw < H;
+  const int h = h_raw < H ? h_raw : H - 1;
   const int b = blockIdx.y;
   const PairDesc d = desc[b];
   const GatherSet gather{d, h};
-  solve_front_warp(valid, gather, rec + ((size_t)b * H + (size_t)blockIdx.x * 32) * kRecDoubles,
-                   min(32, H - (int)blockIdx.x * 32), sB, sR, sOk);
+  solve_front_warp(valid, gather, rec + ((size_t)b * H + first) * kRecDoubles, min(spw, H - first), sB, sR, sOk, spw);
 }
 
 __global__ void __launch_bounds__(64) solve_roots(PairState* __restrict__ state, int H,
@@ -1012,6 +1012,11 @@ static int ensure_workspace(tv5_ctx* ctx, int B, size_t total_pp, size_t total_s
   return TV5_OK;
 }
 
+// fewer sets per warp for small submissions (shorter critical path, more warps), 32 for throughput
+static int front_sets_per_warp(int64_t total_sets) {
+  return total_sets <= 8192 ? 8 : (total_sets <= 16384 ? 16 : 32);
+}
+
 static void stage_mark(tv5_ctx* ctx, cudaStream_t st, int i) {
   if (ctx->profiling) cudaEventRecord(ctx->ev[i], st);
 }
@@ -1291,7 +1296,8 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
     if (allow_fast) prep_points<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_front>>>(desc, state, w.pp);
     if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 1], s_front);
     if (ctx->split_solver) {
-      solve_front<<<dim3((H + 31) / 32, nb), 32, 0, s_front>>>(desc, H, w.rec + so * kRecDoubles);
+      const int spw = front_sets_per_warp((int64_t)nb * H);
+      solve_front<<<dim3((H + spw - 1) / spw, nb), 32, 0, s_front>>>(desc, H, w.rec + so * kRecDoubles, spw);
       solve_roots<<<dim3((H + 63) / 64, nb), 64, 0, s_front>>>(state, H, w.rec + so * kRecDoubles,
                                                                (RootEntry*)w.entries + so * 10, w.n_roots + so,
                                                                w.n_valid + so);
@@ -1526,7 +1532,8 @@ int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, i
     if ((rc = ensure_workspace(ctx, 1, 1, (size_t)H))) return rc;
     TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, &d, sizeof(d), cudaMemcpyHostToDevice, st));
     TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState), st));
-    solve_front<<<dim3((H + 31) / 32, 1), 32, 0, st>>>(w.desc, H, w.rec);
+    const int spw = front_sets_per_warp(H);
+    solve_front<<<dim3((H + spw - 1) / spw, 1), 32, 0, st>>>(w.desc, H, w.rec, spw);
     solve_roots<<<dim3((H + 63) / 64, 1), 64, 0, st>>>(w.state, H, w.rec, (RootEntry*)w.entries, n_roots, n_valid);
     solve_poses<<<dim3((H * 10 + 127) / 128, 1), 128, 0, st>>>(w.desc, w.state, H, with_cheirality, w.rec,
                                                               (const RootEntry*)w.entries, E_list,
