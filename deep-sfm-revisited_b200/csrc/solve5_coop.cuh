@@ -33,7 +33,8 @@ constexpr int kCoopPointDoubles = 20;
 // One lane's constraint row r of set sw:  sum_t Q_t * L_t  (Q quadratic, L linear in (w,x,y,1))
 //      det row:      Q_t = E(a,1)E(b,2) - E(b,1)E(a,2),  L_t = E(t,0),  (a,b) = (t+1,t+2) mod 3
 //      row (i,j):    Q_t = sum_p E(i,p)E(t,p) - [t==i] tr/2,  L_t = E(t,j)
-__device__ __forceinline__ void coop_build_row(const double (*sB)[kCoopStride], int sw, int gb, bool isdet,
+template <int S>
+__device__ __forceinline__ void coop_build_row(const double (*sB)[S], int sw, int gb, bool isdet,
                                                int ri, int rj, double (&row)[20]) {
   const unsigned FULL = 0xffffffffu;
   double Q[3][10];
@@ -79,7 +80,8 @@ __device__ __forceinline__ void coop_build_row(const double (*sB)[kCoopStride], 
 // sB[e][lane]: basis coefficient e = k*9 + c of the lane's set (k: unknown w,x,y,1; c = 3i+j)
 // sR[e][lane]: e = r*10 + j, r = 0..5 <-> pivot columns 4..9, j <-> matrix columns 10..19
 // kCoopJam rounds (x 3 sets) are carried through the elimination together.
-__device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[kCoopStride], double (*sR)[kCoopStride],
+template <int S>
+__device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[S], double (*sR)[S],
                                                            int* sOk, int lane, int n_sets = 32) {
   const unsigned FULL = 0xffffffffu;
 #if TV5_COOP_SMEM_BROADCAST
@@ -101,8 +103,8 @@ __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[kC
 #pragma unroll
     for (int v = 0; v < kCoopJam; ++v) {
       const int sw_raw = (kCoopJam * round2 + v) * 3 + g;
-      sw[v] = sw_raw < 32 ? sw_raw : 31;
-      active[v] = rowlane && sw_raw < 32;
+      sw[v] = sw_raw < n_sets ? sw_raw : n_sets - 1;
+      active[v] = rowlane && sw_raw < n_sets;
       coop_build_row(sB, sw[v], gb, isdet, ri, rj, row[v]);
     }
     // ---- Gauss-Jordan with partial pivoting on columns 0..9, rows spread over the group's lanes
@@ -185,7 +187,8 @@ __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[kC
 }
 
 // 3x3 polynomial matrix from the six reduced rows (see hidden_matrix in solve5.cuh)
-__device__ __forceinline__ void hidden_matrix_from_rows(const double (*sR)[kCoopStride], int lane,
+template <int S>
+__device__ __forceinline__ void hidden_matrix_from_rows(const double (*sR)[S], int lane,
                                                         double (&Bp)[3][3][5]) {
 #pragma unroll
   for (int r = 0; r < 3; ++r) {

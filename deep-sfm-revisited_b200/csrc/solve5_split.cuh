@@ -39,10 +39,10 @@ struct RootEntry {                  // one isolated real root
 // sets_per_warp (32, 16 or 8): lanes >= sets_per_warp idle in the per-set phases and the elimination
 // runs ceil(sets_per_warp / 3) rounds — fewer sets per warp shorten the critical path of small
 // submissions (one 4096-set pair: 128 warps x 11 rounds -> 512 warps x 3 rounds).
-template <typename Gather>
+template <int S, typename Gather>
 __device__ __forceinline__ void solve_front_warp(bool valid, const Gather& gather, double* __restrict__ rec_warp,
-                                                 int n_sets_here, double (*sB)[kCoopStride],
-                                                 double (*sR)[kCoopStride], int* sOk, int sets_per_warp = 32) {
+                                                 int n_sets_here, double (*sB)[S],
+                                                 double (*sR)[S], int* sOk, int sets_per_warp = 32) {
   const int lane = threadIdx.x & 31;
   bool ok = valid;
   {
@@ -51,19 +51,23 @@ __device__ __forceinline__ void solve_front_warp(bool valid, const Gather& gathe
     nullspace_basis(q, qp, B);
 #pragma unroll
     for (int c = 0; c < 9; ++c) ok = ok && (fabs(B[3][c]) <= 1.0);  // false on NaN (degenerate set)
+    if (lane < sets_per_warp) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int c = 0; c < 9; ++c) sB[k * 9 + c][lane] = ok ? B[k][c] : (k == 3 ? 1.0 : 0.0);
+        for (int c = 0; c < 9; ++c) sB[k * 9 + c][lane] = ok ? B[k][c] : (k == 3 ? 1.0 : 0.0);
+    }
   }
   __syncwarp();
   coop_constraints_eliminate(sB, sR, sOk, lane, sets_per_warp);
   __syncwarp();
-  ok = ok && (lane < sets_per_warp) && sOk[lane];
+  ok = ok && (lane < sets_per_warp) && sOk[min(lane, sets_per_warp - 1)];
   {
     double Bp[3][3][5], poly[11];
-    hidden_matrix_from_rows(sR, lane, Bp);
+    const int col = min(lane, sets_per_warp - 1);   // idle lanes read a valid column, write nothing
+    hidden_matrix_from_rows(sR, col, Bp);
     hidden_determinant(Bp, poly);
+    if (lane < sets_per_warp) {
     // park Bp, poly and the flag in this lane's column of sR (its rows are consumed)
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -76,6 +80,7 @@ __device__ __forceinline__ void solve_front_warp(bool valid, const Gather& gathe
     for (int i = 0; i < 11; ++i) sR[46 + i][lane] = ok ? poly[i] : 0.0;
     sR[57][lane] = 0.0;
     sR[58][lane] = ok ? 1.0 : 0.0;
+    }
   }
   __syncwarp();
   // coalesced copy-out: lanes walk the 96 doubles of one record

@@ -257,19 +257,31 @@ __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ de
 // ------------------------------------------------------------------------------------------
 // split solver (solve5_split.cuh): solve_front -> solve_roots -> solve_poses
 // ------------------------------------------------------------------------------------------
+// SPW = sets per warp (32, 16 or 8); shared memory is sized for SPW lanes (stride SPW + 1), so the
+// 16-set form fits 11 warps per SM (register limit) where the 32-set form fits 8.
+template <int SPW>
 __global__ void __launch_bounds__(32) solve_front(const PairDesc* __restrict__ desc, int H,
-                                                  double* __restrict__ rec, int spw) {
-  __shared__ double sB[kCoopBasisDoubles][kCoopStride];
-  __shared__ double sR[kCoopRowsDoubles][kCoopStride];
+                                                  double* __restrict__ rec) {
+  constexpr int S = SPW + 1;
+  __shared__ double sB[kCoopBasisDoubles][S];
+  __shared__ double sR[kCoopRowsDoubles][S];
   __shared__ int sOk[32];
-  const int first = blockIdx.x * spw;                 // spw = sets per warp (32, 16 or 8)
+  const int first = blockIdx.x * SPW;
   const int h_raw = first + threadIdx.x;
-  const bool valid = (int)threadIdx.x < spw && h_raw < H;
+  const bool valid = (int)threadIdx.x < SPW && h_raw < H;
   const int h = h_raw < H ? h_raw : H - 1;
   const int b = blockIdx.y;
   const PairDesc d = desc[b];
   const GatherSet gather{d, h};
-  solve_front_warp(valid, gather, rec + ((size_t)b * H + first) * kRecDoubles, min(spw, H - first), sB, sR, sOk, spw);
+  solve_front_warp<S>(valid, gather, rec + ((size_t)b * H + first) * kRecDoubles, min(SPW, H - first), sB, sR, sOk,
+                      SPW);
+}
+
+static void launch_solve_front(int spw, int H, int nb, cudaStream_t st, const PairDesc* desc, double* rec) {
+  const dim3 grid((H + spw - 1) / spw, nb);
+  if (spw == 8) solve_front<8><<<grid, 32, 0, st>>>(desc, H, rec);
+  else if (spw == 16) solve_front<16><<<grid, 32, 0, st>>>(desc, H, rec);
+  else solve_front<32><<<grid, 32, 0, st>>>(desc, H, rec);
 }
 
 __global__ void __launch_bounds__(64) solve_roots(PairState* __restrict__ state, int H,
@@ -1014,6 +1026,7 @@ static int ensure_workspace(tv5_ctx* ctx, int B, size_t total_pp, size_t total_s
 
 // fewer sets per warp for small submissions (shorter critical path, more warps), 32 for throughput
 static int front_sets_per_warp(int64_t total_sets) {
+  if (const char* e = getenv("TV5_FRONT_SPW")) return atoi(e) == 8 ? 8 : (atoi(e) == 16 ? 16 : 32);   // dev knob
   return total_sets <= 8192 ? 8 : (total_sets <= 16384 ? 16 : 32);
 }
 
@@ -1297,7 +1310,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
     if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 1], s_front);
     if (ctx->split_solver) {
       const int spw = front_sets_per_warp((int64_t)nb * H);
-      solve_front<<<dim3((H + spw - 1) / spw, nb), 32, 0, s_front>>>(desc, H, w.rec + so * kRecDoubles, spw);
+      launch_solve_front(spw, H, nb, s_front, desc, w.rec + so * kRecDoubles);
       solve_roots<<<dim3((H + 63) / 64, nb), 64, 0, s_front>>>(state, H, w.rec + so * kRecDoubles,
                                                                (RootEntry*)w.entries + so * 10, w.n_roots + so,
                                                                w.n_valid + so);
@@ -1533,7 +1546,7 @@ int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, i
     TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, &d, sizeof(d), cudaMemcpyHostToDevice, st));
     TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState), st));
     const int spw = front_sets_per_warp(H);
-    solve_front<<<dim3((H + spw - 1) / spw, 1), 32, 0, st>>>(w.desc, H, w.rec, spw);
+    launch_solve_front(spw, H, 1, st, w.desc, w.rec);
     solve_roots<<<dim3((H + 63) / 64, 1), 64, 0, st>>>(w.state, H, w.rec, (RootEntry*)w.entries, n_roots, n_valid);
     solve_poses<<<dim3((H * 10 + 127) / 128, 1), 128, 0, st>>>(w.desc, w.state, H, with_cheirality, w.rec,
                                                               (const RootEntry*)w.entries, E_list,
