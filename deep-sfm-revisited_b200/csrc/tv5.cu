@@ -986,7 +986,20 @@ static int grow_same(tv5_ctx* ctx, T*& p, size_t old_cap, size_t new_cap) {
   return TV5_OK;
 }
 
+static int ensure_workspace_impl(tv5_ctx* ctx, int B, size_t total_pp, size_t total_sets);
 static int ensure_workspace(tv5_ctx* ctx, int B, size_t total_pp, size_t total_sets) {
+  Workspace& w = ctx->ws;
+  const void* before[4] = {w.desc, w.pp, w.E_list, w.hyp};
+  const int rc = ensure_workspace_impl(ctx, B, total_pp, total_sets);
+  const void* after[4] = {w.desc, w.pp, w.E_list, w.hyp};
+  if (memcmp(before, after, sizeof(before)) != 0) {   // captured graphs hold the old addresses
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+  }
+  return rc;
+}
+
+static int ensure_workspace_impl(tv5_ctx* ctx, int B, size_t total_pp, size_t total_sets) {
   Workspace& w = ctx->ws;
   int rc;
   if ((size_t)B > w.desc_cap || !w.desc) {
@@ -1164,6 +1177,8 @@ int tv5_destroy(tv5_ctx* ctx) {
   for (int i = 0; i <= TV5_N_STAGES; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (auto e : ctx->prof_ev) cudaEventDestroy(e);
+  for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+  if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
   if (ctx->front_stream) {
     cudaStreamDestroy(ctx->front_stream);
     cudaStreamDestroy(ctx->back_stream);
@@ -1258,190 +1273,235 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
   if (rc) return rc;
   Workspace& w = ctx->ws;
   TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, hd.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, st));
-  TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState) * B, st));
-  const int allow_fast = (two_stage || ctx->force_exact) ? 0 : 1;
-
-  // A submission may be cut into chunks of pairs, each with a front (prep + five-point solve:
-  // float64, latency bound) and a back (scoring: float32 pipe bound, + selection).
-  //  * host-buffer entry point: chunk c runs as soon as its copies have landed (ready_ev), in
-  //    plain order front(c), back(c) on the caller's stream;
-  //  * tv5_set_overlap(1): fronts on a low-priority and backs on a high-priority internal stream,
-  //    so the solver of chunk c+1 runs in the shadow of the scorer of chunk c.  Measured on B200
-  //    (DESIGN.md section 4.4): no gain — solver warps make almost no progress next to the
-  //    FFMA2-saturating scorer — hence off by default.
-  int n_chunks = 1;
-  if (ready_ev && !two_stage) n_chunks = n_ready;        // compute chunks = copy chunks
-  else if (ctx->overlap && !two_stage) n_chunks = std::max(1, std::min(kPipeChunks, B / kPipeMinPairs));
-  const bool two_streams = ctx->overlap && n_chunks > 1;
-  cudaStream_t s_front = st, s_back = st;
-  if (two_streams) {
-    if ((rc = ensure_pipe_streams(ctx))) return rc;
-    s_front = ctx->front_stream;
-    s_back = ctx->back_stream;
-    TV5_CUDA(ctx, cudaEventRecord(ctx->pipe_entry, st));
-    TV5_CUDA(ctx, cudaStreamWaitEvent(s_front, ctx->pipe_entry, 0));
-    TV5_CUDA(ctx, cudaStreamWaitEvent(s_back, ctx->pipe_entry, 0));
-  }
-  std::vector<int> first((size_t)n_chunks + 1);
-  for (int c = 0; c <= n_chunks; ++c)
-    first[c] = (ready_ev && n_chunks == n_ready) ? ready_first[c] : (int)((int64_t)B * c / n_chunks);
-  const int slots = TV5_SCORE_MINB * ctx->sm_count;
-  const bool prof = ctx->profiling;
-  if (prof && (rc = ensure_prof_events(ctx, n_chunks))) return rc;
-  ctx->prof_chunks = prof ? n_chunks : 0;
-
-  // ---- front: prep + solve of one chunk
-  auto front = [&](int c) -> int {
-    const int b0 = first[c], nb = first[c + 1] - b0;
-    int cmax_pp = 0;
-    for (int b = b0; b < b0 + nb; ++b) cmax_pp = std::max(cmax_pp, (hd[b].n + 1) / 2);
-    const PairDesc* desc = w.desc + b0;
-    PairState* state = w.state + b0;
-    const size_t so = (size_t)b0 * H;
-    if (ready_ev) {  // inputs of this chunk: every host chunk up to the one holding its last pair
-      int k = 0;
-      while (k + 1 < n_ready && ready_first[k + 1] < b0 + nb) ++k;
-      for (int j = (c == 0 ? 0 : k); j <= k; ++j) TV5_CUDA(ctx, cudaStreamWaitEvent(s_front, ready_ev[j], 0));
-    }
-    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 0], s_front);
-    prep_norms<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_front>>>(desc, state);
-    band_consts<<<(nb + 127) / 128, 128, 0, s_front>>>(desc, state, nb, thr, allow_fast);
-    if (allow_fast) prep_points<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_front>>>(desc, state, w.pp);
-    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 1], s_front);
-    if (ctx->split_solver) {
-      const int spw = front_sets_per_warp((int64_t)nb * H);
-      launch_solve_front(spw, H, nb, s_front, desc, w.rec + so * kRecDoubles);
-      solve_roots<<<dim3((H + 63) / 64, nb), 64, 0, s_front>>>(state, H, w.rec + so * kRecDoubles,
-                                                               (RootEntry*)w.entries + so * 10, w.n_roots + so,
-                                                               w.n_valid + so);
-      solve_poses<<<dim3((H * 10 + 127) / 128, nb), 128, 0, s_front>>>(
-          desc, state, H, with_cheirality, w.rec + so * kRecDoubles, (const RootEntry*)w.entries + so * 10,
-          w.E_list + so * 90, with_cheirality ? w.P_list + so * 120 : nullptr, w.n_valid + so, w.hyp + so * 10,
-          w.hyp_id + so * 10, w.notin + so * 10, w.out + so * 10);
-    } else {
-      solve_sets<<<dim3((H + 31) / 32, nb), 32, 0, s_front>>>(
-          desc, state, H, with_cheirality, w.E_list + so * 90, with_cheirality ? w.P_list + so * 120 : nullptr,
-          w.n_valid + so, w.n_roots + so, w.hyp + so * 10, w.hyp_id + so * 10, w.notin + so * 10, w.out + so * 10);
-    }
-    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 2], s_front);
-    if (two_streams) TV5_CUDA(ctx, cudaEventRecord(ctx->pipe_solved[c], s_front));
-    return TV5_OK;
-  };
-  // ---- back: scoring + selection of one chunk
-  auto back = [&](int c) -> int {
-    const int b0 = first[c], nb = first[c + 1] - b0;
-    int cmax_pp = 0;
-    for (int b = b0; b < b0 + nb; ++b) cmax_pp = std::max(cmax_pp, (hd[b].n + 1) / 2);
-    PairDesc* desc = w.desc + b0;
-    PairState* state = w.state + b0;
-    Control* ctl = w.ctl + c;
-    const size_t so = (size_t)b0 * H;
-    const double* E_list = w.E_list + so * 90;
-    const double* P_list = with_cheirality ? w.P_list + so * 120 : nullptr;
-    const Hyp32* hyp = w.hyp + so * 10;
-    int32_t* hyp_id = w.hyp_id + so * 10;
-    uint32_t* notin = w.notin + so * 10;
-    uint32_t* out = w.out + so * 10;
-    int32_t* cand = w.cand + so * 10;
-    int32_t* cand_cnt = w.cand_cnt + so * 10;
-    if (two_streams) TV5_CUDA(ctx, cudaStreamWaitEvent(s_back, ctx->pipe_solved[c], 0));
-    // tile size: big tiles for batches, enough tiles to balance 2 CTAs/SM for a single pair
-    int pp_per_tile = kMaxTilePairs;
-    {
-      const double est_M = (double)H * (with_cheirality ? 3.0 : 4.5);
-      const double n_hc = std::max(1.0, est_M / kHypChunk);
-      const double want_pc = 6.0 * slots / (n_hc * nb);
-      if (want_pc > 1.0) {
-        int t = (int)((double)cmax_pp / want_pc);
-        t = (t + 7) & ~7;
-        pp_per_tile = std::max(64, std::min(kMaxTilePairs, t));
+  // ---- single pair: the fixed launch sequence is captured once per (N, iterations, flags) into a
+  //      CUDA graph and replayed (one graph launch instead of a memset and 13 kernel launches);
+  //      the descriptor with the caller's pointers is uploaded outside the graph, so one graph
+  //      serves every call of that shape.
+  const bool want_graph = ctx->use_graphs && B == 1 && !ready_ev && !ctx->profiling && !ctx->overlap && !two_stage;
+  GraphKey gkey{hd[0].n, iters, with_cheirality, (int)ctx->split_solver | ((int)ctx->early_exit << 1) |
+                                                      ((int)ctx->force_exact << 2) | ((P_out != nullptr) << 3), thr};
+  if (want_graph) {
+    for (auto& g : ctx->graphs)
+      if (g.key == gkey) {
+        TV5_CUDA(ctx, cudaGraphLaunch(g.exec, st));
+        return TV5_OK;
       }
+  }
+  cudaStream_t sx = st;   // the stream the work is enqueued on (the capture stream while a graph is built)
+  auto enqueue_all = [&]() -> int {
+  TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState) * B, sx));
+    const int allow_fast = (two_stage || ctx->force_exact) ? 0 : 1;
+  
+    // A submission may be cut into chunks of pairs, each with a front (prep + five-point solve:
+    // float64, latency bound) and a back (scoring: float32 pipe bound, + selection).
+    //  * host-buffer entry point: chunk c runs as soon as its copies have landed (ready_ev), in
+    //    plain order front(c), back(c) on the caller's stream;
+    //  * tv5_set_overlap(1): fronts on a low-priority and backs on a high-priority internal stream,
+    //    so the solver of chunk c+1 runs in the shadow of the scorer of chunk c.  Measured on B200
+    //    (DESIGN.md section 4.4): no gain — solver warps make almost no progress next to the
+    //    FFMA2-saturating scorer — hence off by default.
+    int n_chunks = 1;
+    if (ready_ev && !two_stage) n_chunks = n_ready;        // compute chunks = copy chunks
+    else if (ctx->overlap && !two_stage) n_chunks = std::max(1, std::min(kPipeChunks, B / kPipeMinPairs));
+    const bool two_streams = ctx->overlap && n_chunks > 1;
+    cudaStream_t s_front = sx, s_back = sx;
+    if (two_streams) {
+      if ((rc = ensure_pipe_streams(ctx))) return rc;
+      s_front = ctx->front_stream;
+      s_back = ctx->back_stream;
+      TV5_CUDA(ctx, cudaEventRecord(ctx->pipe_entry, sx));
+      TV5_CUDA(ctx, cudaStreamWaitEvent(s_front, ctx->pipe_entry, 0));
+      TV5_CUDA(ctx, cudaStreamWaitEvent(s_back, ctx->pipe_entry, 0));
     }
-    const int X = std::max(1, std::min(4096, (4 * ctx->sm_count + nb - 1) / nb));
-    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 3], s_back);
-    // staging only pays when the scoring work dwarfs the extra launches (~10 small kernels)
-    const bool staged = ctx->early_exit && allow_fast && !two_stage &&
-                        (double)nb * H * 3.0 * (2.0 * cmax_pp) >= 2.0e8;
-    if (staged) {
-      // staged scoring with exact pruning (see set_stage / stage_leader / prune_compact)
-      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 4], s_back);
-      const Hyp32* alt_hyp = w.hyp2 + so * 10;
-      const int32_t* alt_id = w.hyp_id2 + so * 10;
-      const uint32_t* alt_out = w.out2 + so * 10;
-      const int n_stages = ctx->early_stages;
-      for (int stg = 0; stg < n_stages; ++stg) {
-        set_stage<<<(nb + 127) / 128, 128, 0, s_back>>>(desc, state, nb, ctx->early_frac[stg], ctx->early_frac[stg + 1], stg == 0,
-                                                        pp_per_tile);
-        if (stg == 0) {
-          plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile, kHypChunk);
+    std::vector<int> first((size_t)n_chunks + 1);
+    for (int c = 0; c <= n_chunks; ++c)
+      first[c] = (ready_ev && n_chunks == n_ready) ? ready_first[c] : (int)((int64_t)B * c / n_chunks);
+    const int slots = TV5_SCORE_MINB * ctx->sm_count;
+    const bool prof = ctx->profiling;
+    if (prof && (rc = ensure_prof_events(ctx, n_chunks))) return rc;
+    ctx->prof_chunks = prof ? n_chunks : 0;
+  
+    // ---- front: prep + solve of one chunk
+    auto front = [&](int c) -> int {
+      const int b0 = first[c], nb = first[c + 1] - b0;
+      int cmax_pp = 0;
+      for (int b = b0; b < b0 + nb; ++b) cmax_pp = std::max(cmax_pp, (hd[b].n + 1) / 2);
+      const PairDesc* desc = w.desc + b0;
+      PairState* state = w.state + b0;
+      const size_t so = (size_t)b0 * H;
+      if (ready_ev) {  // inputs of this chunk: every host chunk up to the one holding its last pair
+        int k = 0;
+        while (k + 1 < n_ready && ready_first[k + 1] < b0 + nb) ++k;
+        for (int j = (c == 0 ? 0 : k); j <= k; ++j) TV5_CUDA(ctx, cudaStreamWaitEvent(s_front, ready_ev[j], 0));
+      }
+      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 0], s_front);
+      prep_norms<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_front>>>(desc, state);
+      band_consts<<<(nb + 127) / 128, 128, 0, s_front>>>(desc, state, nb, thr, allow_fast);
+      if (allow_fast) prep_points<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_front>>>(desc, state, w.pp);
+      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 1], s_front);
+      if (ctx->split_solver) {
+        const int spw = front_sets_per_warp((int64_t)nb * H);
+        launch_solve_front(spw, H, nb, s_front, desc, w.rec + so * kRecDoubles);
+        solve_roots<<<dim3((H + 63) / 64, nb), 64, 0, s_front>>>(state, H, w.rec + so * kRecDoubles,
+                                                                 (RootEntry*)w.entries + so * 10, w.n_roots + so,
+                                                                 w.n_valid + so);
+        solve_poses<<<dim3((H * 10 + 127) / 128, nb), 128, 0, s_front>>>(
+            desc, state, H, with_cheirality, w.rec + so * kRecDoubles, (const RootEntry*)w.entries + so * 10,
+            w.E_list + so * 90, with_cheirality ? w.P_list + so * 120 : nullptr, w.n_valid + so, w.hyp + so * 10,
+            w.hyp_id + so * 10, w.notin + so * 10, w.out + so * 10);
+      } else {
+        solve_sets<<<dim3((H + 31) / 32, nb), 32, 0, s_front>>>(
+            desc, state, H, with_cheirality, w.E_list + so * 90, with_cheirality ? w.P_list + so * 120 : nullptr,
+            w.n_valid + so, w.n_roots + so, w.hyp + so * 10, w.hyp_id + so * 10, w.notin + so * 10, w.out + so * 10);
+      }
+      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 2], s_front);
+      if (two_streams) TV5_CUDA(ctx, cudaEventRecord(ctx->pipe_solved[c], s_front));
+      return TV5_OK;
+    };
+    // ---- back: scoring + selection of one chunk
+    auto back = [&](int c) -> int {
+      const int b0 = first[c], nb = first[c + 1] - b0;
+      int cmax_pp = 0;
+      for (int b = b0; b < b0 + nb; ++b) cmax_pp = std::max(cmax_pp, (hd[b].n + 1) / 2);
+      PairDesc* desc = w.desc + b0;
+      PairState* state = w.state + b0;
+      Control* ctl = w.ctl + c;
+      const size_t so = (size_t)b0 * H;
+      const double* E_list = w.E_list + so * 90;
+      const double* P_list = with_cheirality ? w.P_list + so * 120 : nullptr;
+      const Hyp32* hyp = w.hyp + so * 10;
+      int32_t* hyp_id = w.hyp_id + so * 10;
+      uint32_t* notin = w.notin + so * 10;
+      uint32_t* out = w.out + so * 10;
+      int32_t* cand = w.cand + so * 10;
+      int32_t* cand_cnt = w.cand_cnt + so * 10;
+      if (two_streams) TV5_CUDA(ctx, cudaStreamWaitEvent(s_back, ctx->pipe_solved[c], 0));
+      // tile size: big tiles for batches, enough tiles to balance 2 CTAs/SM for a single pair
+      int pp_per_tile = kMaxTilePairs;
+      {
+        const double est_M = (double)H * (with_cheirality ? 3.0 : 4.5);
+        const double n_hc = std::max(1.0, est_M / kHypChunk);
+        const double want_pc = 6.0 * slots / (n_hc * nb);
+        if (want_pc > 1.0) {
+          int t = (int)((double)cmax_pp / want_pc);
+          t = (t + 7) & ~7;
+          pp_per_tile = std::max(64, std::min(kMaxTilePairs, t));
+        }
+      }
+      const int X = std::max(1, std::min(4096, (4 * ctx->sm_count + nb - 1) / nb));
+      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 3], s_back);
+      // staging only pays when the scoring work dwarfs the extra launches (~10 small kernels)
+      const bool staged = ctx->early_exit && allow_fast && !two_stage &&
+                          (double)nb * H * 3.0 * (2.0 * cmax_pp) >= 2.0e8;
+      if (staged) {
+        // staged scoring with exact pruning (see set_stage / stage_leader / prune_compact)
+        if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 4], s_back);
+        const Hyp32* alt_hyp = w.hyp2 + so * 10;
+        const int32_t* alt_id = w.hyp_id2 + so * 10;
+        const uint32_t* alt_out = w.out2 + so * 10;
+        const int n_stages = ctx->early_stages;
+        for (int stg = 0; stg < n_stages; ++stg) {
+          set_stage<<<(nb + 127) / 128, 128, 0, s_back>>>(desc, state, nb, ctx->early_frac[stg], ctx->early_frac[stg + 1], stg == 0,
+                                                          pp_per_tile);
+          if (stg == 0) {
+            plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile, kHypChunk);
+            score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
+                                                                    notin, out);
+          } else {  // few survivors per pair: 256-slot hypothesis chunks
+            plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile, kScoreThreads);
+            score_bounds<false, 1><<<4 * ctx->sm_count, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile,
+                                                                                   w.pp, hyp, notin, out);
+          }
+          if (stg + 1 < n_stages) {
+            stage_leader<<<nb, 1024, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
+            exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
+            prune_compact<<<nb, 256, 0, s_back>>>(desc, state, H, hyp, hyp_id, out, cand_cnt, (Hyp32*)alt_hyp,
+                                                  (int32_t*)alt_id, (uint32_t*)alt_out);
+            std::swap(hyp, alt_hyp);
+            { const int32_t* t = hyp_id; hyp_id = (int32_t*)alt_id; alt_id = t; }
+            { const uint32_t* t = out; out = (uint32_t*)alt_out; alt_out = t; }
+          }
+        }
+        if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 5], s_back);
+      } else {
+        plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile, kHypChunk);
+        if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 4], s_back);
+        if (allow_fast)
           score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
                                                                   notin, out);
-        } else {  // few survivors per pair: 256-slot hypothesis chunks
-          plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile, kScoreThreads);
-          score_bounds<false, 1><<<4 * ctx->sm_count, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile,
-                                                                                 w.pp, hyp, notin, out);
-        }
-        if (stg + 1 < n_stages) {
-          stage_leader<<<nb, 1024, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
-          exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
-          prune_compact<<<nb, 256, 0, s_back>>>(desc, state, H, hyp, hyp_id, out, cand_cnt, (Hyp32*)alt_hyp,
-                                                (int32_t*)alt_id, (uint32_t*)alt_out);
-          std::swap(hyp, alt_hyp);
-          { const int32_t* t = hyp_id; hyp_id = (int32_t*)alt_id; alt_id = t; }
-          { const uint32_t* t = out; out = (uint32_t*)alt_out; alt_out = t; }
-        }
+        if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 5], s_back);
       }
-      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 5], s_back);
-    } else {
-      plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile, kHypChunk);
-      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 4], s_back);
-      if (allow_fast)
-        score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
-                                                                notin, out);
-      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 5], s_back);
-    }
-    pick_top<<<nb, 1024, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
-    if (two_stage) {
-      // (single chunk) stage A runs on n_pre points: exact_counts reads n_full, so the descriptors
-      // are re-uploaded with n_full := n_pre for this stage and restored afterwards.
-      std::vector<PairDesc> ha = hd;
-      for (auto& d : ha) d.n_full = d.n_pre;
-      TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, ha.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, s_back));
-      exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
-      set_winners<<<nb, 256, 0, s_back>>>(desc, state, H, hyp_id, cand, cand_cnt, w.cand + w.sets_cap * 10);
-      TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, hd.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, s_back));
-      exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
-    } else {
-      exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
-      if (allow_fast) {
-        pick_rest<<<nb, 1024, 0, s_back>>>(desc, state, H, out, cand, cand_cnt);
+      pick_top<<<nb, 1024, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
+      if (two_stage) {
+        // (single chunk) stage A runs on n_pre points: exact_counts reads n_full, so the descriptors
+        // are re-uploaded with n_full := n_pre for this stage and restored afterwards.
+        std::vector<PairDesc> ha = hd;
+        for (auto& d : ha) d.n_full = d.n_pre;
+        TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, ha.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, s_back));
         exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
+        set_winners<<<nb, 256, 0, s_back>>>(desc, state, H, hyp_id, cand, cand_cnt, w.cand + w.sets_cap * 10);
+        TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, hd.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, s_back));
+        exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
+      } else {
+        exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
+        if (allow_fast) {
+          pick_rest<<<nb, 1024, 0, s_back>>>(desc, state, H, out, cand, cand_cnt);
+          exact_counts<<<dim3(X, nb), 256, 0, s_back>>>(desc, state, H, thr, E_list, hyp_id, cand, cand_cnt);
+        }
+      }
+      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 6], s_back);
+      finalize<<<nb, 256, 0, s_back>>>(desc, state, H, thr, E_list, P_list, hyp_id, cand, cand_cnt,
+                                       ctx->split_solver ? w.n_valid + so : nullptr);
+      if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 7], s_back);
+      return TV5_OK;
+    };
+    if (two_streams) {
+      for (int c = 0; c < n_chunks; ++c)
+        if ((rc = front(c))) return rc;
+      for (int c = 0; c < n_chunks; ++c)
+        if ((rc = back(c))) return rc;
+    } else {
+      for (int c = 0; c < n_chunks; ++c) {
+        if ((rc = front(c))) return rc;
+        if ((rc = back(c))) return rc;
       }
     }
-    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 6], s_back);
-    finalize<<<nb, 256, 0, s_back>>>(desc, state, H, thr, E_list, P_list, hyp_id, cand, cand_cnt,
-                                     ctx->split_solver ? w.n_valid + so : nullptr);
-    if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 7], s_back);
+    if (two_streams) {
+      TV5_CUDA(ctx, cudaEventRecord(ctx->pipe_done, s_back));
+      TV5_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->pipe_done, 0));
+    }
+  if (prof) ctx->ev_pending = true;
+    TV5_CUDA(ctx, cudaGetLastError());
     return TV5_OK;
   };
-  if (two_streams) {
-    for (int c = 0; c < n_chunks; ++c)
-      if ((rc = front(c))) return rc;
-    for (int c = 0; c < n_chunks; ++c)
-      if ((rc = back(c))) return rc;
-  } else {
-    for (int c = 0; c < n_chunks; ++c) {
-      if ((rc = front(c))) return rc;
-      if ((rc = back(c))) return rc;
+  if (want_graph) {
+    if (!ctx->cap_stream && cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->use_graphs = false;
+    } else if (cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      sx = ctx->cap_stream;
+      const int rc_cap = enqueue_all();
+      cudaGraph_t graph = nullptr;
+      const cudaError_t e_end = cudaStreamEndCapture(ctx->cap_stream, &graph);
+      cudaGraphExec_t exec = nullptr;
+      if (rc_cap == TV5_OK && e_end == cudaSuccess && graph &&
+          cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+        if (ctx->graphs.size() >= 32) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
+        ctx->graphs.push_back({gkey, exec});
+        TV5_CUDA(ctx, cudaGraphLaunch(exec, st));
+        return TV5_OK;
+      }
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      ctx->use_graphs = false;   // capture is not possible here: plain launches from now on
+      sx = st;
+    } else {
+      cudaGetLastError();
+      ctx->use_graphs = false;
     }
   }
-  if (two_streams) {
-    TV5_CUDA(ctx, cudaEventRecord(ctx->pipe_done, s_back));
-    TV5_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_done, 0));
-  }
-  if (prof) ctx->ev_pending = true;
-  TV5_CUDA(ctx, cudaGetLastError());
-  return TV5_OK;
+  return enqueue_all();
 }
 
 int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, const double* x2,
@@ -1888,6 +1948,12 @@ int tv5_measure_fp32_peak(tv5_ctx* ctx, int mode, double* tflops_out) {
 int tv5_set_force_exact(tv5_ctx* ctx, int on) {
   if (!ctx) return TV5_ERR_INVALID;
   ctx->force_exact = on != 0;
+  return TV5_OK;
+}
+
+int tv5_set_graphs(tv5_ctx* ctx, int on) {
+  if (!ctx) return TV5_ERR_INVALID;
+  ctx->use_graphs = on != 0;
   return TV5_OK;
 }
 

@@ -114,6 +114,16 @@ struct Workspace {
 
 struct RngTable { int N; int iters; int32_t* sets; };
 
+// single-pair launch sequence captured as a CUDA graph, one per shape
+struct GraphKey {
+  int n, iters, cheir, flags;
+  double thr;
+  bool operator==(const GraphKey& o) const {
+    return n == o.n && iters == o.iters && cheir == o.cheir && flags == o.flags && thr == o.thr;
+  }
+};
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; };
+
 }  // namespace tv5
 
 struct tv5_ctx {
@@ -133,6 +143,9 @@ struct tv5_ctx {
   cudaEvent_t start_ev = nullptr;
   int polish_max_ctas = 0;              // co-resident CTAs of irls_polish on this device
   // solver / scorer overlap inside one submission
+  bool use_graphs = true;               // single-pair submissions replay a captured CUDA graph
+  std::vector<tv5::GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
   bool early_exit = false;              // staged scoring with exact hypothesis pruning (opt-in)
   int early_stages = 3;                 // ... stage boundaries as fractions of a pair's points
   float early_frac[tv5::kEarlyMaxStages + 1] = {0.0f, 0.30f, 0.52f, 1.0f};

@@ -426,6 +426,10 @@ class Engine:
     def set_force_exact(self, on=True):
         _check(self.ctx, self.L.tv5_set_force_exact(self.ctx, int(bool(on))), "set_force_exact")
 
+    def set_graphs(self, on=True):
+        """CUDA-graph replay of single-pair submissions (default on)."""
+        _check(self.ctx, self.L.tv5_set_graphs(self.ctx, int(bool(on))), "set_graphs")
+
     def set_early_exit(self, on=True):
         """Staged scoring with exact hypothesis pruning (default off); results do not depend on it."""
         _check(self.ctx, self.L.tv5_set_early_exit(self.ctx, int(bool(on))), "set_early_exit")

@@ -123,6 +123,8 @@ def load_library():
     L.tv5_measure_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.tv5_set_force_exact.restype = C.c_int
     L.tv5_set_force_exact.argtypes = [vp, C.c_int]
+    L.tv5_set_graphs.restype = C.c_int
+    L.tv5_set_graphs.argtypes = [vp, C.c_int]
     L.tv5_set_early_exit.restype = C.c_int
     L.tv5_set_early_exit.argtypes = [vp, C.c_int]
     L.tv5_set_split_solver.restype = C.c_int

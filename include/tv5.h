@@ -263,6 +263,11 @@ int tv5_plane_sweep(tv5_ctx* ctx, void* stream, const float* ref_feat, const flo
  * tests use this to prove it. */
 int tv5_set_force_exact(tv5_ctx* ctx, int on);
 
+/* CUDA graphs (default on): a single-pair submission (tv5_compute_pose, the shape SFMnet calls) replays a
+ * graph captured once per (N, iterations, flags) instead of issuing its memset and 13 kernel launches one
+ * by one; on = 0 issues plain launches. */
+int tv5_set_graphs(tv5_ctx* ctx, int on);
+
 /* Early exit (opt-in, default off): the correspondences are scored in three stages (30 %, 52 %, 100 % of
  * each pair's points); after a stage every hypothesis whose upper bound on its FULL inlier count —
  * unseen points counted as inliers — is below the exact count of an actual hypothesis is dropped.

@@ -882,3 +882,29 @@ def test_flow_pose_sweep_chain_recovers_scene_depth(engine):
     step = gt[inner] ** 2 / L
     err = np.abs(depth[inner] - gt[inner])
     assert np.median(err / step) < 0.6 and (err < 1.5 * step).mean() > 0.9
+
+
+def test_cuda_graph_replay_equals_plain_launches(engine, std_pair):
+    """Single-pair submissions replay a captured CUDA graph: same results as plain launches, for
+    changing input/output pointers, after the workspace has been re-allocated by a bigger batch, and
+    for several shapes in the cache."""
+    sc, x1, x2 = std_pair
+    sets = dev(synth.make_sets(10000, 4096, 31), torch.int32)
+    try:
+        engine.set_graphs(False)
+        plain = engine.compute_pose(x1, x2, 8, THR, sets=sets, want_mask=True)
+        plain_small = engine.compute_pose(x1[:777].contiguous(), x2[:777].contiguous(), 2, THR)
+    finally:
+        engine.set_graphs(True)
+    a = engine.compute_pose(x1, x2, 8, THR, sets=sets, want_mask=True)           # capture
+    b = engine.compute_pose(x1.clone(), x2.clone(), 8, THR, sets=sets.clone(), want_mask=True)   # replay, new pointers
+    small = engine.compute_pose(x1[:777].contiguous(), x2[:777].contiguous(), 2, THR)            # second shape
+    # a large batch at 16 iterations re-allocates the workspace: cached graphs must be dropped
+    big = [synth.make_pair(3000, seed=900 + i) for i in range(24)]
+    engine.compute_pose_batch(dev(np.concatenate([p["x1"] for p in big])), dev(np.concatenate([p["x2"] for p in big])),
+                              np.arange(25) * 3000, 16, THR)
+    c = engine.compute_pose(x1, x2, 8, THR, sets=sets, want_mask=True)           # re-capture
+    for r in (a, b, c):
+        assert torch.equal(r.E, plain.E) and torch.equal(r.P, plain.P) and torch.equal(r.mask, plain.mask)
+        assert torch.equal(r.stats[:5], plain.stats[:5])
+    assert torch.equal(small.E, plain_small.E) and small.count == plain_small.count
