@@ -1280,12 +1280,22 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
   const bool want_graph = ctx->use_graphs && B == 1 && !ready_ev && !ctx->profiling && !ctx->overlap && !two_stage;
   GraphKey gkey{hd[0].n, iters, with_cheirality, (int)ctx->split_solver | ((int)ctx->early_exit << 1) |
                                                       ((int)ctx->force_exact << 2) | ((P_out != nullptr) << 3), thr};
+  bool build_graph = false;
   if (want_graph) {
     for (auto& g : ctx->graphs)
       if (g.key == gkey) {
         TV5_CUDA(ctx, cudaGraphLaunch(g.exec, st));
         return TV5_OK;
       }
+    // capturing costs about a millisecond: only shapes that keep coming back are captured (SFMnet's
+    // keypoint counts change from pair to pair; its dense crop does not)
+    bool seen = false;
+    for (auto& e : ctx->graph_seen)
+      if (e.key == gkey) { seen = true; build_graph = ++e.count >= 3; break; }
+    if (!seen) {
+      if (ctx->graph_seen.size() >= 64) ctx->graph_seen.erase(ctx->graph_seen.begin());
+      ctx->graph_seen.push_back({gkey, 1});
+    }
   }
   cudaStream_t sx = st;   // the stream the work is enqueued on (the capture stream while a graph is built)
   auto enqueue_all = [&]() -> int {
@@ -1474,7 +1484,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
     TV5_CUDA(ctx, cudaGetLastError());
     return TV5_OK;
   };
-  if (want_graph) {
+  if (want_graph && build_graph) {
     if (!ctx->cap_stream && cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
       cudaGetLastError();
       ctx->use_graphs = false;

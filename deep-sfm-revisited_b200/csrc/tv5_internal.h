@@ -123,6 +123,7 @@ struct GraphKey {
   }
 };
 struct GraphEntry { GraphKey key; cudaGraphExec_t exec; };
+struct GraphSeen { GraphKey key; int count; };
 
 }  // namespace tv5
 
@@ -145,6 +146,7 @@ struct tv5_ctx {
   // solver / scorer overlap inside one submission
   bool use_graphs = true;               // single-pair submissions replay a captured CUDA graph
   std::vector<tv5::GraphEntry> graphs;
+  std::vector<tv5::GraphSeen> graph_seen;   // shapes seen so far; captured on the third occurrence
   cudaStream_t cap_stream = nullptr;
   bool early_exit = false;              // staged scoring with exact hypothesis pruning (opt-in)
   int early_stages = 3;                 // ... stage boundaries as fractions of a pair's points
