@@ -909,3 +909,22 @@ def test_cuda_graph_replay_equals_plain_launches(engine, std_pair):
         assert torch.equal(r.E, plain.E) and torch.equal(r.P, plain.P) and torch.equal(r.mask, plain.mask)
         assert torch.equal(r.stats[:5], plain.stats[:5])
     assert torch.equal(small.E, plain_small.E) and small.count == plain_small.count
+
+
+def test_early_exit_single_large_pair_with_graph_replay(engine):
+    """One large pair is staged too (enough work) and, as a single-pair submission, goes through the
+    CUDA-graph replay: four identical calls with early exit == the full scoring."""
+    sc = synth.make_pair(120000, seed=77)
+    x1, x2 = dev(sc["x1"]), dev(sc["x2"])
+    sets = dev(synth.make_sets(120000, 4096, 78), torch.int32)
+    full = engine.compute_pose(x1, x2, 8, THR, sets=sets, want_mask=True)
+    try:
+        engine.set_early_exit(True)
+        runs = [engine.compute_pose(x1, x2, 8, THR, sets=sets, want_mask=True) for _ in range(4)]
+    finally:
+        engine.set_early_exit(False)
+    for r in runs:
+        assert torch.equal(r.E, full.E) and torch.equal(r.P, full.P) and torch.equal(r.mask, full.mask)
+        assert torch.equal(r.stats[:4], full.stats[:4])
+    again = engine.compute_pose(x1, x2, 8, THR, sets=sets, want_mask=True)   # back to full scoring: other graph key
+    assert torch.equal(again.E, full.E) and torch.equal(again.stats[:5], full.stats[:5])
