@@ -26,7 +26,10 @@ constexpr int kScoreThreads = 256;   // threads per scoring CTA
 constexpr int kHypPerThread = TV5_HYP_PER_THREAD;  // hypotheses held in registers per thread
 constexpr int kHypChunk = kScoreThreads * kHypPerThread;
 constexpr int kScoreUnroll = TV5_SCORE_UNROLL;
-constexpr int kMaxTilePairs = 512;   // point pairs staged in shared memory per tile (24 KB)
+#ifndef TV5_TILE_PAIRS
+#define TV5_TILE_PAIRS 512
+#endif
+constexpr int kMaxTilePairs = TV5_TILE_PAIRS;   // point pairs staged in shared memory per tile (24 KB)
 constexpr int kExactChunk = 2048;    // points per work item of the float64 scorer
 constexpr int kHostChunks = 8;       // pipeline depth of the host-buffer entry point
 constexpr int kPipeChunks = 8;       // chunks of pairs of one submission (solver / scorer overlap)
