@@ -822,38 +822,36 @@ __global__ void __launch_bounds__(256) set_winners(PairDesc* __restrict__ desc,
                                                    int32_t* __restrict__ cand,
                                                    int32_t* __restrict__ cand_cnt,
                                                    int32_t* __restrict__ scratch) {
-  // Stage A left cand[i] = i (all hypotheses) and cand_cnt[i] = count on n_pre points.
-  // A hypothesis survives if no hypothesis of the same set has a larger count, or an equal
-  // count and a smaller root index.  Hypotheses of one set occupy consecutive slots.
+  // Stage A left cand[i] = i (all hypotheses) and cand_cnt[i] = count on n_pre points.  Per
+  // minimal set the reference keeps the FIRST maximum over its roots (kernel_functions.cu:
+  // 186-202, strict >).  Slots are handed out by atomicAdd in arbitrary order, so the roots of a
+  // set are found by set id, never by slot adjacency: every hypothesis folds the key
+  // ((count+1) << 4 | 15 - root) into its set's cell with atomicMax; the hypothesis whose key
+  // equals the cell is the set's winner (unique: the root index is part of the key).
   const int b = blockIdx.x;
   PairState& s = state[b];
   const size_t base = (size_t)b * H * 10;
-  const size_t sbase = (size_t)b * H * 20;  // scratch: [H*10] flags + [H*10] compacted list
+  const size_t sbase = (size_t)b * H * 20;  // scratch: [H] per-set keys, then [H*10] winner slots
+  int32_t* set_key = scratch + sbase;
+  int32_t* list = scratch + sbase + (size_t)H * 10;
   const int M = s.M;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) set_key[h] = 0;
+  __syncthreads();
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
-    const int id = hyp_id[base + m], set = id >> 4, root = id & 15, cnt = cand_cnt[base + m];
-    bool win = true;
-    for (int j = m - root; j < M && j <= m - root + 9; ++j) {
-      if (j == m || j < 0) continue;
-      const int jd = hyp_id[base + j];
-      if ((jd >> 4) != set) continue;
-      const int jc = cand_cnt[base + j];
-      if (jc > cnt || (jc == cnt && (jd & 15) < root)) win = false;
-    }
-    scratch[sbase + m] = win ? 1 : 0;
+    const int id = hyp_id[base + m];
+    atomicMax(&set_key[id >> 4], ((cand_cnt[base + m] + 1) << 4) | (15 - (id & 15)));
   }
   __syncthreads();
   if (threadIdx.x == 0) { s.n_cand = 0; s.exact_from = 0; }
   __syncthreads();
-  for (int m = threadIdx.x; m < M; m += blockDim.x)
-    if (scratch[sbase + m]) {
-      const int i = atomicAdd(&s.n_cand, 1);
-      scratch[sbase + (size_t)H * 10 + i] = m;
-    }
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const int id = hyp_id[base + m];
+    if (set_key[id >> 4] == (((cand_cnt[base + m] + 1) << 4) | (15 - (id & 15)))) list[atomicAdd(&s.n_cand, 1)] = m;
+  }
   __syncthreads();
   const int nc = s.n_cand;
   for (int i = threadIdx.x; i < nc; i += blockDim.x) {
-    cand[base + i] = scratch[sbase + (size_t)H * 10 + i];
+    cand[base + i] = list[i];
     cand_cnt[base + i] = 0;
   }
 }
@@ -912,6 +910,31 @@ __global__ void ref_rng_kernel(int N, int iters, int32_t* __restrict__ sets) {
       int idx = (int)truncf(r);
       sets[((size_t)gi * iters + it) * 5 + i] = min(idx, N - 1);
     }
+}
+
+// The curand_uniform stream of the reference does not depend on N (kernel_functions.cu:269-278 scales
+// the draw afterwards), so the draws are generated once per context — draw-major, u[d*512 + tid] =
+// d-th draw of reference thread tid, which makes the table for `iters` a prefix of every longer
+// one — and each submission only applies the reference's float32 scaling for its own N on the
+// stream: no allocation, no synchronisation, no curand_init per call.
+__global__ void ref_rng_uniform_kernel(int draws, float* __restrict__ u) {
+  const int gi = threadIdx.x + blockDim.x * blockIdx.x;
+  curandState st;
+  curand_init(1234ULL, gi, 0, &st);
+  for (int d = 0; d < draws; ++d) u[(size_t)d * TV5_REF_THREADS + gi] = curand_uniform(&st);
+}
+
+// grid (ceil(H*5/256), B): sets[b][h][k] for h = tid*iters + it  <-  draw it*5+k of thread tid
+__global__ void __launch_bounds__(256) rng_scale_sets(const PairDesc* __restrict__ desc, int H, int iters,
+                                                      const float* __restrict__ u, int32_t* __restrict__ sets) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * 5) return;
+  const int N = desc[blockIdx.y].n;
+  const int h = i / 5, k = i - 5 * h, tid = h / iters, it = h - tid * iters;
+  float r = u[(size_t)(it * 5 + k) * TV5_REF_THREADS + tid];
+  r *= ((N - 1) - 0 + 0.999999f);
+  r += 0;
+  sets[(size_t)blockIdx.y * H * 5 + i] = min((int)truncf(r), N - 1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1003,34 +1026,41 @@ static int ensure_workspace_impl(tv5_ctx* ctx, int B, size_t total_pp, size_t to
   Workspace& w = ctx->ws;
   int rc;
   if ((size_t)B > w.desc_cap || !w.desc) {
-    size_t nc = std::max((size_t)B, w.desc_cap * 2);
-    if ((rc = grow_same(ctx, w.desc, w.desc_cap, nc))) return rc;
-    if ((rc = grow_same(ctx, w.state, w.desc_cap, nc))) return rc;
+    const size_t oc = w.desc_cap;
+    const size_t nc = std::max((size_t)B, oc * 2);
+    w.desc_cap = 0;
+    if ((rc = grow_same(ctx, w.desc, oc, nc))) return rc;
+    if ((rc = grow_same(ctx, w.state, oc, nc))) return rc;
     w.desc_cap = nc;
   }
   if (!w.ctl && cudaMalloc(&w.ctl, sizeof(Control) * kPipeChunks) != cudaSuccess) return TV5_ERR_NOMEM;
   if ((rc = grow(ctx, w.pp, w.pp_cap, total_pp))) return rc;
   if (total_sets > w.sets_cap || !w.E_list) {
-    size_t nc = std::max(total_sets, w.sets_cap + w.sets_cap / 2);
-    if ((rc = grow_same(ctx, w.E_list, w.sets_cap * 90, nc * 90))) return rc;
-    if ((rc = grow_same(ctx, w.P_list, w.sets_cap * 120, nc * 120))) return rc;
-    if ((rc = grow_same(ctx, w.n_valid, w.sets_cap, nc))) return rc;
-    if ((rc = grow_same(ctx, w.n_roots, w.sets_cap, nc))) return rc;
-    if ((rc = grow_same(ctx, w.rec, w.sets_cap * kRecDoubles, nc * kRecDoubles))) return rc;
-    {
-      RootEntry* en = (RootEntry*)w.entries;
-      if ((rc = grow_same(ctx, en, w.sets_cap * 10, nc * 10))) { w.entries = nullptr; return rc; }
-      w.entries = en;
-    }
-    if ((rc = grow_same(ctx, w.hyp, w.sets_cap * 10, nc * 10))) return rc;
-    if ((rc = grow_same(ctx, w.hyp_id, w.sets_cap * 10, nc * 10))) return rc;
-    if ((rc = grow_same(ctx, w.notin, w.sets_cap * 10, nc * 10))) return rc;
-    if ((rc = grow_same(ctx, w.out, w.sets_cap * 10, nc * 10))) return rc;
-    if ((rc = grow_same(ctx, w.hyp2, w.sets_cap * 10, nc * 10))) return rc;
-    if ((rc = grow_same(ctx, w.hyp_id2, w.sets_cap * 10, nc * 10))) return rc;
-    if ((rc = grow_same(ctx, w.out2, w.sets_cap * 10, nc * 10))) return rc;
-    if ((rc = grow_same(ctx, w.cand, w.sets_cap * 30, nc * 30))) return rc;  // + 2x set_winners scratch
-    if ((rc = grow_same(ctx, w.cand_cnt, w.sets_cap * 10, nc * 10))) return rc;
+    const size_t oc = w.sets_cap;
+    const size_t nc = std::max(total_sets, oc + oc / 2);
+    // All per-set buffers change size together.  If any allocation fails, the capacity is reset to
+    // zero so that the next call reallocates every one of them (grow_same frees what is still
+    // held): a later, smaller submission can never run on a mix of old- and new-sized buffers.
+    w.sets_cap = 0;
+    w.hyp_cap = 0;
+    RootEntry* en = (RootEntry*)w.entries;
+    rc = grow_same(ctx, w.E_list, oc * 90, nc * 90);
+    if (!rc) rc = grow_same(ctx, w.P_list, oc * 120, nc * 120);
+    if (!rc) rc = grow_same(ctx, w.n_valid, oc, nc);
+    if (!rc) rc = grow_same(ctx, w.n_roots, oc, nc);
+    if (!rc) rc = grow_same(ctx, w.rec, oc * kRecDoubles, nc * kRecDoubles);
+    if (!rc) { rc = grow_same(ctx, en, oc * 10, nc * 10); w.entries = en; }
+    if (!rc) rc = grow_same(ctx, w.hyp, oc * 10, nc * 10);
+    if (!rc) rc = grow_same(ctx, w.hyp_id, oc * 10, nc * 10);
+    if (!rc) rc = grow_same(ctx, w.notin, oc * 10, nc * 10);
+    if (!rc) rc = grow_same(ctx, w.out, oc * 10, nc * 10);
+    if (!rc) rc = grow_same(ctx, w.hyp2, oc * 10, nc * 10);
+    if (!rc) rc = grow_same(ctx, w.hyp_id2, oc * 10, nc * 10);
+    if (!rc) rc = grow_same(ctx, w.out2, oc * 10, nc * 10);
+    if (!rc) rc = grow_same(ctx, w.cand, oc * 30, nc * 30);  // + 2x set_winners scratch
+    if (!rc) rc = grow_same(ctx, w.cand_cnt, oc * 10, nc * 10);
+    if (!rc) rc = grow_same(ctx, w.rng_sets, oc * 5, nc * 5);
+    if (rc) return rc;
     w.sets_cap = nc;
     w.hyp_cap = nc * 10;
   }
@@ -1163,12 +1193,13 @@ int tv5_destroy(tv5_ctx* ctx) {
   cudaSetDevice(ctx->device);
   Workspace& w = ctx->ws;
   void* ptrs[] = {w.desc, w.state, w.ctl, w.pp, w.E_list, w.P_list, w.n_valid, w.n_roots, w.rec, w.entries, w.hyp,
-                  w.hyp_id, w.notin, w.out, w.hyp2, w.hyp_id2, w.out2, w.cand, w.cand_cnt, w.h2d_x, w.h2d_sets, w.out_E,
+                  w.hyp_id, w.notin, w.out, w.hyp2, w.hyp_id2, w.out2, w.cand, w.cand_cnt, w.rng_sets, w.h2d_x, w.h2d_sets, w.out_E,
                   w.out_P, w.out_res, w.polish_jobs, w.polish_partial, w.polish_barrier,
                   w.polish_x, w.polish_E, w.flow_jobs, w.flow_x, w.flow_EP};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  for (auto& t : ctx->rng_tables) cudaFree(t.sets);
+  if (ctx->rng_u) cudaFree(ctx->rng_u);
+  if (ctx->last_done) cudaEventDestroy(ctx->last_done);
   if (ctx->copy_stream) {
     cudaStreamDestroy(ctx->copy_stream);
     for (auto& e : ctx->chunk_ev) cudaEventDestroy(e);
@@ -1201,25 +1232,46 @@ int tv5_ref_rng_sets(tv5_ctx* ctx, void* stream, int N, int iters, int32_t* sets
   return TV5_OK;
 }
 
-static int cached_rng_table(tv5_ctx* ctx, cudaStream_t st, int N, int iters, const int32_t** out) {
-  for (auto& t : ctx->rng_tables)
-    if (t.N == N && t.iters == iters) { *out = t.sets; return TV5_OK; }
-  if (ctx->rng_tables.size() >= 64) {  // bounded cache
-    // the evicted table may still be in use by work queued on another stream
+// uniform draws of the reference RNG for at least `iters` iterations (see ref_rng_uniform_kernel).
+// Allocates and synchronises only when a longer table than any seen before is needed.
+static int ensure_rng_uniform(tv5_ctx* ctx, cudaStream_t st, int iters, const float** out) {
+  if (ctx->rng_u && ctx->rng_u_iters >= iters) { *out = ctx->rng_u; return TV5_OK; }
+  if (ctx->rng_u) {
+    // the old table may be referenced by queued work and by captured graphs
     TV5_CUDA(ctx, cudaDeviceSynchronize());
-    cudaFree(ctx->rng_tables.front().sets);
-    ctx->rng_tables.erase(ctx->rng_tables.begin());
+    cudaFree(ctx->rng_u);
+    ctx->rng_u = nullptr;
+    ctx->rng_u_iters = 0;
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
   }
-  int32_t* p = nullptr;
-  if (cudaMalloc(&p, (size_t)TV5_REF_THREADS * iters * 5 * sizeof(int32_t)) != cudaSuccess) {
+  const int cap = std::max(iters, 8);
+  if (cudaMalloc(&ctx->rng_u, (size_t)TV5_REF_THREADS * cap * 5 * sizeof(float)) != cudaSuccess) {
+    ctx->rng_u = nullptr;
     ctx->last_cuda = (int)cudaGetLastError();
     return TV5_ERR_NOMEM;
   }
-  ref_rng_kernel<<<8, 64, 0, st>>>(N, iters, p);
-  // make the table visible to work later submitted on other streams
-  TV5_CUDA(ctx, cudaStreamSynchronize(st));
-  ctx->rng_tables.push_back({N, iters, p});
-  *out = p;
+  ref_rng_uniform_kernel<<<8, 64, 0, st>>>(cap * 5, ctx->rng_u);
+  TV5_CUDA(ctx, cudaGetLastError());
+  TV5_CUDA(ctx, cudaStreamSynchronize(st));   // visible to work later submitted on other streams
+  ctx->rng_u_iters = cap;
+  *out = ctx->rng_u;
+  return TV5_OK;
+}
+
+// One context owns one workspace: submissions on different streams are ordered one after the
+// other (the new stream waits for the previous submission's completion event), so two streams — or
+// two host threads taking turns — never race on it.  Concurrent calls from two host threads on the
+// SAME context remain the caller's responsibility (include/tv5.h).
+static int submission_enter(tv5_ctx* ctx, cudaStream_t st) {
+  if (!ctx->last_done) TV5_CUDA(ctx, cudaEventCreateWithFlags(&ctx->last_done, cudaEventDisableTiming));
+  if (ctx->has_last && ctx->last_stream != st) TV5_CUDA(ctx, cudaStreamWaitEvent(st, ctx->last_done, 0));
+  return TV5_OK;
+}
+static int submission_leave(tv5_ctx* ctx, cudaStream_t st) {
+  TV5_CUDA(ctx, cudaEventRecord(ctx->last_done, st));
+  ctx->last_stream = st;
+  ctx->has_last = true;
   return TV5_OK;
 }
 
@@ -1252,12 +1304,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
     d.n_pre = n_pre <= 0 ? n : std::min(n_pre, n);
     d.n_full = n_full <= 0 ? n : std::min(n_full, n);
     if (d.n_pre != d.n_full) two_stage = true;
-    if (sets) {
-      d.sets = sets + (size_t)b * H * 5;
-    } else {
-      int rc = cached_rng_table(ctx, st, n, iters, &d.sets);
-      if (rc) return rc;
-    }
+    d.sets = sets ? sets + (size_t)b * H * 5 : nullptr;   // reference RNG table: filled in below
     d.E_out = E_out + 9 * (size_t)b;
     d.P_out = P_out ? P_out + 12 * (size_t)b : nullptr;
     d.result = result + b;
@@ -1272,6 +1319,12 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
   int rc = ensure_workspace(ctx, B, total_pp, (size_t)B * H);
   if (rc) return rc;
   Workspace& w = ctx->ws;
+  const float* rng_u = nullptr;
+  if (!sets) {
+    if ((rc = ensure_rng_uniform(ctx, st, iters, &rng_u))) return rc;
+    for (int b = 0; b < B; ++b) hd[b].sets = w.rng_sets + (size_t)b * H * 5;
+  }
+  if ((rc = submission_enter(ctx, st))) return rc;
   TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, hd.data(), sizeof(PairDesc) * B, cudaMemcpyHostToDevice, st));
   // ---- single pair: the fixed launch sequence is captured once per (N, iterations, flags) into a
   //      CUDA graph and replayed (one graph launch instead of a memset and 13 kernel launches);
@@ -1279,13 +1332,13 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
   //      serves every call of that shape.
   const bool want_graph = ctx->use_graphs && B == 1 && !ready_ev && !ctx->profiling && !ctx->overlap && !two_stage;
   GraphKey gkey{hd[0].n, iters, with_cheirality, (int)ctx->split_solver | ((int)ctx->early_exit << 1) |
-                                                      ((int)ctx->force_exact << 2) | ((P_out != nullptr) << 3), thr};
+                                                      ((int)ctx->force_exact << 2) | ((P_out != nullptr) << 3) | ((sets == nullptr) << 4), thr};
   bool build_graph = false;
   if (want_graph) {
     for (auto& g : ctx->graphs)
       if (g.key == gkey) {
         TV5_CUDA(ctx, cudaGraphLaunch(g.exec, st));
-        return TV5_OK;
+        return submission_leave(ctx, st);
       }
     // capturing costs about a millisecond: only shapes that keep coming back are captured (SFMnet's
     // keypoint counts change from pair to pair; its dense crop does not)
@@ -1349,6 +1402,8 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
       band_consts<<<(nb + 127) / 128, 128, 0, s_front>>>(desc, state, nb, thr, allow_fast);
       if (allow_fast) prep_points<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_front>>>(desc, state, w.pp);
       if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 1], s_front);
+      if (rng_u) rng_scale_sets<<<dim3((H * 5 + 255) / 256, nb), 256, 0, s_front>>>(desc, H, iters, rng_u,
+                                                                                   w.rng_sets + so * 5);
       if (ctx->split_solver) {
         const int spw = front_sets_per_warp((int64_t)nb * H);
         launch_solve_front(spw, H, nb, s_front, desc, w.rec + so * kRecDoubles);
@@ -1500,7 +1555,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
         if (ctx->graphs.size() >= 32) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
         ctx->graphs.push_back({gkey, exec});
         TV5_CUDA(ctx, cudaGraphLaunch(exec, st));
-        return TV5_OK;
+        return submission_leave(ctx, st);
       }
       if (graph) cudaGraphDestroy(graph);
       cudaGetLastError();
@@ -1511,7 +1566,8 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
       ctx->use_graphs = false;
     }
   }
-  return enqueue_all();
+  if ((rc = enqueue_all())) return rc;
+  return submission_leave(ctx, st);
 }
 
 int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, const double* x2,

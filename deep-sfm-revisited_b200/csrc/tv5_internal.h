@@ -97,6 +97,7 @@ struct Workspace {
   uint32_t* out2 = nullptr;
   int32_t* cand = nullptr;                            // [B*H*10]  hypothesis slots to re-score
   int32_t* cand_cnt = nullptr;                        // [B*H*10]  exact counts of the candidates
+  int32_t* rng_sets = nullptr;                        // [B*H*5]   reference-RNG index tables of this submission
   // staging for the host-buffer entry point
   double* h2d_x = nullptr;   size_t h2d_cap = 0;      // [2 * sum n * 2]
   int32_t* h2d_sets = nullptr; size_t h2d_sets_cap = 0;
@@ -114,8 +115,6 @@ struct Workspace {
   double* flow_x = nullptr; size_t flow_x_cap = 0;             // x1 | x2 of tv5_pose_from_flow
   double* flow_EP = nullptr; size_t flow_EP_cap = 0;           // [B,9] | [B,12] float64 results
 };
-
-struct RngTable { int N; int iters; int32_t* sets; };
 
 // single-pair launch sequence captured as a CUDA graph, one per shape
 struct GraphKey {
@@ -135,7 +134,11 @@ struct tv5_ctx {
   int sm_count = 0;
   int last_cuda = 0;
   tv5::Workspace ws;
-  std::vector<tv5::RngTable> rng_tables;
+  float* rng_u = nullptr;               // uniform draws of the reference RNG, [rng_u_iters*5][512]
+  int rng_u_iters = 0;
+  cudaStream_t last_stream = nullptr;   // stream of the previous submission (cross-stream ordering)
+  cudaEvent_t last_done = nullptr;
+  bool has_last = false;
   bool force_exact = false;
   bool profiling = false;
   cudaEvent_t ev[TV5_N_STAGES + 1] = {};

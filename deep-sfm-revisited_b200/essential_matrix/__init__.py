@@ -89,13 +89,45 @@ class LazyCount:
         return format(self._get(), spec)
 
 
+def _check_input_init(x, name):
+    # CHECK_INPUT_INIT, essential_matrix_wrapper.cpp:39-42 (same order, same wording)
+    if not isinstance(x, _torch.Tensor) or not x.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if x.dtype != _torch.float64:
+        raise RuntimeError(f"{name} must be a double tensor")
+    if not x.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def _ransac(input1, input2, num_test_points, num_ransac_test_points, num_ransac_iterations,
+            inlier_threshold, with_cheirality):
+    _check_input_init(input1, "input1")
+    _check_input_init(input2, "input2")
+    eng = _tv5.get_engine(input1.device)
+    iters, thr = int(num_ransac_iterations), float(inlier_threshold)
+    if input1.dim() == 2 and input1.shape[1] == 2:
+        return eng.compute_pose(input1, input2, iters, thr, n_pre=int(num_test_points),
+                                n_full=int(num_ransac_test_points), with_cheirality=with_cheirality)
+    # Any other shape: the reference takes num_points = input1.size(0) for SAMPLING
+    # (essential_matrix.cu:118,199) and reads both tensors as flat (x, y) arrays, scoring the first
+    # num_test_points / num_ransac_test_points of them.  epipolar_utils.compute_E_matrix calls it
+    # this way with [1, n, 2] tensors (epipolar_utils.py:70-73), i.e. every minimal set is five
+    # times point 0.  Same rule here: minimal sets from the reference RNG table of size(0) points,
+    # scoring domain clipped to the points actually present (the reference would read past the end).
+    if input1.numel() % 2 or input1.numel() < 2 or input2.numel() != input1.numel():
+        raise RuntimeError("input1 and input2 must hold the same number of (x, y) rows")
+    rows = max(int(input1.shape[0]), 1) if input1.dim() else 1
+    flat1, flat2 = input1.view(-1, 2), input2.view(-1, 2)
+    sets = eng.ref_rng_sets(rows, iters)
+    return eng.compute_pose(flat1, flat2, iters, thr, n_pre=int(num_test_points),
+                            n_full=int(num_ransac_test_points), sets=sets, with_cheirality=with_cheirality)
+
+
 def computeP(input1, input2, num_test_points, num_ransac_test_points, num_ransac_iterations,
              inlier_threshold):
     """essential_matrix.computeP — ProjectionMatrixRansacWrapper, wrapper.cpp:59-71."""
-    r = _tv5.get_engine(getattr(input1, "device", None) if getattr(input1, "is_cuda", False) else None) \
-        .compute_pose(input1, input2, int(num_ransac_iterations), float(inlier_threshold),
-                      n_pre=int(num_test_points), n_full=int(num_ransac_test_points),
-                      with_cheirality=True)
+    r = _ransac(input1, input2, num_test_points, num_ransac_test_points, num_ransac_iterations,
+                inlier_threshold, True)
     return r.E, r.P, LazyCount(r)
 
 
@@ -104,11 +136,8 @@ def initialise(input1, input2, num_test_points, num_ransac_test_points, num_rans
     """essential_matrix.initialise — EssentialMatrixInitialiseWrapper, wrapper.cpp:45-57.
     (The reference also prints the inlier count on every call, essential_matrix.cu:170; this
     implementation never prints.)"""
-    r = _tv5.get_engine(getattr(input1, "device", None) if getattr(input1, "is_cuda", False) else None) \
-        .compute_pose(input1, input2, int(num_ransac_iterations), float(inlier_threshold),
-                      n_pre=int(num_test_points), n_full=int(num_ransac_test_points),
-                      with_cheirality=False)
-    return r.E
+    return _ransac(input1, input2, num_test_points, num_ransac_test_points, num_ransac_iterations,
+                   inlier_threshold, False).E
 
 
 def _require_double_contiguous(x, name):

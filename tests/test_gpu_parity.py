@@ -151,18 +151,24 @@ def _compare_solver(mine, ref_E, ref_P, ref_nr, ref_nv, skip=2, same_regime=Fals
     ok[:skip] = False
     nr, nv = mine["n_roots"].cpu().numpy(), mine["n_valid"].cpu().numpy()
     same = (nr == ref_nr) & (nv == ref_nv)
-    assert same[ok].mean() >= (0.995 if same_regime else 0.98)   # real-root / cheirality counts
     sel = ok & same
     E = mine["E"].cpu().numpy().reshape(H, 10, 9)
     P = mine["P"].cpu().numpy().reshape(H, 10, 12)
     dE = np.abs(E - ref_E).reshape(H, -1).max(1)[sel] / (np.abs(ref_E).reshape(H, -1).max(1)[sel] + 1)
     dP = np.abs(P - ref_P).reshape(H, -1).max(1)[sel]
+    stats = dict(same_counts=float(same[ok].mean()), dE_le_1e6=float((dE < 1e-6).mean()), dP_le_1e6=float((dP < 1e-6).mean()),
+                 dE_med=float(np.median(dE)), dE_max=float(dE.max()), dP_max=float(dP.max()), dE_q97=float(np.quantile(dE, 0.97)))
+    print("SOLVER_STATS", "gpu" if same_regime else "host", stats)
+    # thresholds sit just below what was measured on B200: against the
+    # reference compiled for the GPU 100 % equal counts and 98.4-99.5 % of solutions within 1e-6
+    assert same[ok].mean() >= (0.999 if same_regime else 0.985)   # real-root / cheirality counts
     # unnormalised E equal in scale, sign and order
     assert np.median(dE) < 1e-9 and np.median(dP) < 1e-9
-    assert (dE < 1e-6).mean() > 0.93 and (dP < 1e-6).mean() > 0.93
     if same_regime:
+        assert (dE < 1e-6).mean() >= 0.98 and (dP < 1e-6).mean() >= 0.98
         assert dE.max() < 1e-3 and dP.max() < 5e-3
     else:
+        assert (dE < 1e-6).mean() >= 0.96 and (dP < 1e-6).mean() >= 0.96
         assert np.quantile(dE, 0.97) < 1e-3
 
 
@@ -293,27 +299,74 @@ def test_pipeline_is_deterministic_and_batch_equals_single(engine):
         _check_self_consistent(engine, pairs[i]["x1"], pairs[i]["x2"], rs, THR)
 
 
-def test_two_stage_selection_matches_oracle(engine, gold):
+def _reference_rule_two_stage(engine, x1h, x2h, sets, thr, n_pre, n_full):
+    """The reference's selection (kernel_functions.cu:184-219 + essential_matrix.cu:252) applied by
+    the CPU oracle's bit-exact scorer to the solutions of OUR solver: per set the first maximum
+    over roots on n_pre points, that root re-scored on n_full points, first maximum over sets
+    (strict >, starting from 0).  Integer work on identical E bits -> the pipeline must agree
+    exactly, whatever the solver's rounding."""
+    sol = engine.solve5(dev(x1h), dev(x2h), dev(sets, torch.int32))
+    E = sol["E"].cpu().numpy().reshape(-1, 10, 9)
+    nv = sol["n_valid"].cpu().numpy()
+    best = (0, -1, -1)
+    for h in range(E.shape[0]):
+        if nv[h] == 0:
+            continue
+        pre = oracle.score(x1h, x2h, E[h, :nv[h]], thr, n=n_pre)
+        j, top = 0, 0
+        for r in range(nv[h]):
+            if pre[r] > top:
+                top, j = int(pre[r]), r
+        full = int(oracle.score(x1h, x2h, E[h, j:j + 1], thr, n=n_full)[0])
+        if full > best[0]:
+            best = (full, h, j)
+    return best, E
+
+
+@pytest.mark.parametrize("split", [1, 0])
+def test_two_stage_selection_matches_reference_rule(engine, gold, split):
+    """n_pre != n_full (kernel_functions.cu:186-215): all-float64 route.  (count, set, root) equal the
+    reference rule exactly; repeated calls are identical (slot order is arbitrary, results are not)."""
     x1h, x2h = gold["kitti_x1"], gold["kitti_x2"]
     sets = synth.make_sets(2000, 512, 71)
-    for n_pre, n_full in ((100, 2000), (2000, 500), (10, 1000)):
-        r = engine.compute_pose(dev(x1h), dev(x2h), 1, THR, n_pre=n_pre, n_full=n_full, sets=dev(sets, torch.int32),
-                                want_mask=True)
-        o = oracle.ransac(x1h, x2h, sets, 1, THR, n_pre=n_pre, n_full=n_full)
-        assert r.fast_path == 0
-        _check_self_consistent(engine, x1h, x2h, r, THR, n_full=n_full)
-        assert abs(r.count - o["count"]) <= 2
-        assert (r.best_set, r.best_root) == (o["best_set"], o["best_root"]) or abs(r.count - o["count"]) <= 2
+    engine.set_split_solver(bool(split))
+    try:
+        for n_pre, n_full in ((100, 2000), (2000, 500), (10, 1000), (37, 38)):
+            (cnt, h, j), E = _reference_rule_two_stage(engine, x1h, x2h, sets, THR, n_pre, n_full)
+            runs = [engine.compute_pose(dev(x1h), dev(x2h), 1, THR, n_pre=n_pre, n_full=n_full,
+                                        sets=dev(sets, torch.int32), want_mask=True) for _ in range(3)]
+            for r in runs:
+                assert r.fast_path == 0
+                assert (r.count, r.best_set, r.best_root) == (cnt, h, j)                 # integer: exact
+                assert (r.E.cpu().numpy().reshape(9) == E[h, j]).all()                   # the winner's own bits
+                _check_self_consistent(engine, x1h, x2h, r, THR, n_full=n_full)
+            o = oracle.ransac(x1h, x2h, sets, 1, THR, n_pre=n_pre, n_full=n_full)
+            # against the oracle's own solver the hypotheses differ in the last bits (SURVEY H2):
+            # counts within 2, and the same winner whenever the counts agree
+            assert abs(cnt - o["count"]) <= 2
+    finally:
+        engine.set_split_solver(True)
 
 
 def test_no_inliers_gives_zero_result(engine):
+    """Defined divergence from the reference's uninitialised output: no hypothesis with
+    an inlier -> count 0, best_set -1, E = P = 0.  NaN coordinates make every Sampson value NaN,
+    i.e. an outlier (kernel_functions.cu:194 `error <= thr`), on the float64 route."""
+    x1h = np.full((200, 2), np.nan)
+    x2h = np.full((200, 2), np.nan)
+    r = engine.compute_pose(dev(x1h), dev(x2h), 1, THR, sets=dev(synth.make_sets(200, 512, 1), torch.int32),
+                            want_mask=True)
+    assert r.count == 0 and r.best_set == -1 and r.best_root == -1 and r.fast_path == 0
+    assert float(r.E.abs().sum()) == 0.0 and float(r.P.abs().sum()) == 0.0 and int(r.mask.sum()) == 0
+    # finite points, threshold far below the rounding of the five sample residuals: the winner, if
+    # any, is whatever the exact float64 scorer says about its own E
     rng = np.random.default_rng(3)
     x1h, x2h = rng.uniform(-1, 1, (200, 2)), rng.uniform(-1, 1, (200, 2))
-    r = engine.compute_pose(dev(x1h), dev(x2h), 1, 1e-12, sets=dev(synth.make_sets(200, 512, 1), torch.int32))
+    r = engine.compute_pose(dev(x1h), dev(x2h), 1, 1e-300, sets=dev(synth.make_sets(200, 512, 1), torch.int32))
     if r.count == 0:
         assert r.best_set == -1 and float(r.E.abs().sum()) == 0.0
     else:
-        _check_self_consistent(engine, x1h, x2h, r, 1e-12)
+        _check_self_consistent(engine, x1h, x2h, r, 1e-300)
 
 
 def test_reference_rng_default_and_reference_extension_golden(engine, std_pair, gold, gold_gpu):
@@ -347,6 +400,35 @@ def test_full_size_dense_pair_properties(engine):
     P = r.P.cpu().numpy()
     assert synth.rotation_error_deg(P[:, :3], sc["R"]) < 0.05 and synth.translation_error_deg(P[:, 3], sc["t"]) < 0.5
     assert r.count > 0.6 * sc["inlier_gt"].sum()
+
+
+def test_config4_full_size_counts_equal_reference_scorer(engine):
+    """configs[3] at its full size — 453,620 dense correspondences x 16,384 minimal sets — checked
+    against the REFERENCE's own ComputeError<double> compiled by nvcc (oracle/_ref/libref_twin_cuda.so,
+    reference sources included verbatim): every hypothesis of our solver is scored by the reference
+    scorer on the GPU box, the reference's first-maximum rule is applied on the host, and the
+    pipeline's (count, set, root) must be that winner exactly (guard-band scorer included)."""
+    import ref_twin
+    T = ref_twin.load()
+    if T is None:
+        pytest.skip("oracle/_ref/libref_twin_cuda.so not built")
+    sc = synth.make_pair(dense=True, seed=4)
+    n = sc["x1"].shape[0]
+    assert n == 453620
+    x1, x2 = dev(sc["x1"]), dev(sc["x2"])
+    sets = dev(synth.make_sets(n, 16384, 9), torch.int32)
+    r = engine.compute_pose(x1, x2, 32, THR, sets=sets)
+    sol = engine.solve5(x1, x2, sets)
+    nv = sol["n_valid"]
+    valid = torch.arange(10, device="cuda")[None, :] < nv[:, None]
+    E_list = sol["E"].reshape(-1, 10, 9)[valid].contiguous()
+    ids = (torch.arange(16384, device="cuda")[:, None] * 16 + torch.arange(10, device="cuda")[None, :])[valid]
+    assert E_list.shape[0] == r.n_hypotheses
+    counts = ref_twin.score(T, x1, x2, n, E_list, THR)            # the reference's scorer, FP64
+    best = int(counts.max())
+    first = int(ids[counts == best].min())                          # first maximum by (set, root)
+    assert (r.count, r.best_set, r.best_root) == (best, first >> 4, first & 15)
+    assert r.fast_path == 1 and r.n_candidates < 200               # the float32 bound did the pruning
 
 
 # ---------------------------------------------------------------------------------------------

@@ -40,10 +40,11 @@ def test_solver_matches_reference_golden(gold, name):
     # (measured: on the ~2 % of solutions that differ by > 1e-6 both implementations violate the
     # essential-matrix constraints equally, ~1e-7 against ~1e-14 typically)
     assert np.median(rel) < 1e-9
-    assert (rel < 1e-6).mean() > 0.93 and rel.max() < 1e-2
+    # measured on these fixtures: 94.7-100 % within 1e-6, worst 5.8e-5 (thresholds sit just below)
+    assert (rel < 1e-6).mean() >= 0.94 and rel.max() < 5e-4
     dP = np.abs(mine["P"] - gold[f"{name}_P"]).reshape(len(sets), -1).max(1)[ok]
     assert np.median(dP) < 1e-9
-    assert (dP < 1e-6).mean() > 0.93 and dP.max() < 1e-2
+    assert (dP < 1e-6).mean() >= 0.94 and dP.max() < 5e-4
 
 
 def test_degenerate_sets_are_harmless(gold):
