@@ -19,9 +19,25 @@ namespace tv5 {
 #ifndef TV5_COOP_SMEM_BROADCAST
 #define TV5_COOP_SMEM_BROADCAST 0
 #endif
+// 1 = pivot search by one redux.sync (max over the group's 10 lanes) instead of four dependent
+// rotation shuffles.  Measured on B200: MUCH slower (solver 3.32 -> 4.14 ms per 1.05 M sets) — redux.sync
+// with three different member masks in one warp is evidently executed mask by mask.  Off.
+#ifndef TV5_COOP_REDUX
+#define TV5_COOP_REDUX 0
+#endif
+// 1 = every lane takes the reciprocal of its own pivot candidate while the pivot search is in flight
+// and the pivot lane's reciprocal is fetched by one shuffle, instead of fetching the pivot and
+// inverting it afterwards: same value, same operation (bit-identical), a shorter dependent chain.
+// Measured on B200: no gain (solver 3.11 -> 3.16 ms per 1.05 M sets).  Off.
+#ifndef TV5_COOP_SPEC_RCP
+#define TV5_COOP_SPEC_RCP 0
+#endif
 constexpr int kCoopBasisDoubles = 36;
 constexpr int kCoopRowsDoubles = 60;
-constexpr int kCoopJam = 1;      // rounds carried through the elimination together (2 measured slower: spills)
+#ifndef TV5_COOP_JAM
+#define TV5_COOP_JAM 1
+#endif
+constexpr int kCoopJam = TV5_COOP_JAM;      // rounds carried through the elimination together (2 measured slower: spills)
 #ifndef TV5_COOP_STRIDE
 #define TV5_COOP_STRIDE 33
 #endif
@@ -91,6 +107,8 @@ __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[S]
   const int r = lane < 30 ? lane - 10 * g : lane - 20;  // rows 10, 11 do not take part
   const int gb = 10 * g;
   const bool rowlane = r < 10;
+  const unsigned gmask = lane < 30 ? (0x3ffu << gb) : 0xC0000000u;   // lanes 30, 31 reduce among themselves
+  (void)gmask;
   const bool isdet = (r == 0) || !rowlane;
   const int ri = isdet ? 0 : (r - 1) / 3;
   const int rj = isdet ? 0 : (r - 1) - 3 * ri;
@@ -123,6 +141,15 @@ __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[S]
         const float mag = fabsf((float)row[v][c]);
         key[v] = (rowlane && pivcol[v] < 0 && mag == mag) ? ((__float_as_uint(mag) & ~31u) | (unsigned)lane) : 0u;
       }
+#if TV5_COOP_SPEC_RCP
+      double inv_self[kCoopJam];
+#pragma unroll
+      for (int v = 0; v < kCoopJam; ++v) inv_self[v] = __drcp_rn(row[v][c]);   // independent of the search below
+#endif
+#if TV5_COOP_REDUX
+#pragma unroll
+      for (int v = 0; v < kCoopJam; ++v) key[v] = __reduce_max_sync(gmask, key[v]);
+#else
 #pragma unroll
       for (int o = 1; o < 16; o <<= 1) {
         const int src = rowlane ? gb + (r + o) % 10 : gb;
@@ -132,6 +159,7 @@ __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[S]
           key[v] = other > key[v] ? other : key[v];
         }
       }
+#endif
       // The pivot row is NOT normalised while eliminating: with multiplier g = row[c] / pivot (0 on
       // the pivot lane itself) every lane does  row[j] -= g * pivot_row[j]  — one fma per column and
       // no select; the surviving rows are divided by their pivot once, at the end.
@@ -142,9 +170,15 @@ __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[S]
         bl[v] = (key[v] >> 5) ? (int)(key[v] & 31u) : gb;
         const float best = __uint_as_float(key[v] & ~31u);
         bad[v] = bad[v] || !(best > 0.f) || !(best < 3.0e38f);
+#if TV5_COOP_SPEC_RCP
+        const double ipiv = __shfl_sync(FULL, inv_self[v], bl[v]);
+        g_mul[v] = (lane == bl[v]) ? 0.0 : -(row[v][c] * ipiv);
+        if (lane == bl[v]) { pivcol[v] = c; pivval[v] = row[v][c]; }
+#else
         const double piv = __shfl_sync(FULL, row[v][c], bl[v]);
         g_mul[v] = (lane == bl[v]) ? 0.0 : -(row[v][c] * __drcp_rn(piv));
         if (lane == bl[v]) { pivcol[v] = c; pivval[v] = piv; }
+#endif
       }
 #if TV5_COOP_SMEM_BROADCAST
       // pivot row to the group through shared memory, two columns per 128-bit access (half the LSU
@@ -174,6 +208,7 @@ __device__ __forceinline__ void coop_constraints_eliminate(const double (*sB)[S]
 #pragma unroll
     for (int v = 0; v < kCoopJam; ++v) {
       const unsigned badmask = __ballot_sync(FULL, bad[v] && rowlane);
+      __syncwarp();   // sR may alias sB: every lane of the group has finished reading the set's basis
       if (active[v]) {
         if (pivcol[v] >= 4) {
           const double sc = __drcp_rn(pivval[v]);

@@ -257,14 +257,22 @@ __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ de
 // ------------------------------------------------------------------------------------------
 // split solver (solve5_split.cuh): solve_front -> solve_roots -> solve_poses
 // ------------------------------------------------------------------------------------------
-// SPW = sets per warp (32, 16 or 8); shared memory is sized for SPW lanes (stride SPW + 1), so the
-// 16-set form fits 11 warps per SM (register limit) where the 32-set form fits 8.
+// SPW = sets per warp (32, 16 or 8); shared memory is sized for SPW lanes (stride SPW + 1).
+#ifndef TV5_FRONT_ALIAS
+#define TV5_FRONT_ALIAS 1
+#endif
 template <int SPW>
 __global__ void __launch_bounds__(32) solve_front(const PairDesc* __restrict__ desc, int H,
                                                   double* __restrict__ rec) {
   constexpr int S = SPW + 1;
+#if TV5_FRONT_ALIAS
+  __shared__ double sAll[kCoopRowsDoubles][S];   // rows 0..35: a set's basis, later its reduced rows (solve_front_warp)
+  double (*sB)[S] = sAll;
+  double (*sR)[S] = sAll;
+#else
   __shared__ double sB[kCoopBasisDoubles][S];
   __shared__ double sR[kCoopRowsDoubles][S];
+#endif
   __shared__ int sOk[32];
   const int first = blockIdx.x * SPW;
   const int h_raw = first + threadIdx.x;
@@ -912,6 +920,70 @@ __global__ void ref_rng_kernel(int N, int iters, int32_t* __restrict__ sets) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// hypothesis-sharded single pair: 192-byte winner record per GPU, first-maximum pick over G records
+// ------------------------------------------------------------------------------------------
+struct WinnerRecord {
+  unsigned long long key;   // count << 32 | ~(global set * 16 + root); 0 = no hypothesis with an inlier
+  double E[9];
+  double P[12];
+  int32_t n_hyp, n_cand, fast, pad;
+};
+static_assert(sizeof(WinnerRecord) == TV5_WINNER_RECORD_BYTES, "record layout");
+
+__global__ void winner_record(const double* __restrict__ E, const double* __restrict__ P,
+                              const tv5_result* __restrict__ res, int set_offset, WinnerRecord* __restrict__ out) {
+  const int t = threadIdx.x;
+  const tv5_result r = *res;
+  const bool have = r.count > 0 && r.best_set >= 0;
+  if (t < 9) out->E[t] = E[t];
+  if (t < 12) out->P[t] = P ? P[t] : 0.0;
+  if (t == 0) {
+    const uint32_t id = (uint32_t)(r.best_set + set_offset) * 16u + (uint32_t)r.best_root;
+    out->key = have ? (((unsigned long long)(uint32_t)r.count << 32) | (0xFFFFFFFFu - id)) : 0ull;
+    out->n_hyp = r.n_hypotheses;
+    out->n_cand = r.n_candidates;
+    out->fast = r.fast_path;
+    out->pad = 0;
+  }
+}
+
+__global__ void winner_pick(const WinnerRecord* __restrict__ recs, int G, double* __restrict__ E_out,
+                            double* __restrict__ P_out, tv5_result* __restrict__ res_out) {
+  // one warp: lane g folds records g, g + 32, ...; ids are unique across ranks, so the maximum key is too
+  const int lane = threadIdx.x;
+  unsigned long long key = 0ull;
+  int n_hyp = 0, n_cand = 0, fast = 1;
+  for (int g = lane; g < G; g += 32) {
+    key = recs[g].key > key ? recs[g].key : key;
+    n_hyp += recs[g].n_hyp;
+    n_cand += recs[g].n_cand;
+    fast &= recs[g].fast;
+  }
+  const unsigned long long best = warp_max(key);
+  n_hyp = warp_sum(n_hyp);
+  n_cand = warp_sum(n_cand);
+  fast = __all_sync(0xffffffffu, fast);
+  int owner = -1;
+  for (int g = lane; g < G; g += 32)
+    if (best != 0ull && recs[g].key == best) owner = g;
+  owner = warp_max(owner);
+  if (lane < 9) E_out[lane] = owner >= 0 ? recs[owner].E[lane] : 0.0;
+  if (P_out && lane < 12) P_out[lane] = owner >= 0 ? recs[owner].P[lane] : 0.0;
+  if (lane == 0) {
+    tv5_result r;
+    const uint32_t id = 0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull);
+    r.count = (int32_t)(best >> 32);
+    r.best_set = owner >= 0 ? (int32_t)(id >> 4) : -1;
+    r.best_root = owner >= 0 ? (int32_t)(id & 15u) : -1;
+    r.n_hypotheses = n_hyp;
+    r.n_candidates = n_cand;
+    r.fast_path = fast;
+    r.reserved[0] = r.reserved[1] = 0;
+    *res_out = r;
+  }
+}
+
 // The curand_uniform stream of the reference does not depend on N (kernel_functions.cu:269-278 scales
 // the draw afterwards), so the draws are generated once per context — draw-major, u[d*512 + tid] =
 // d-th draw of reference thread tid, which makes the table for `iters` a prefix of every longer
@@ -1331,7 +1403,18 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
   //      the descriptor with the caller's pointers is uploaded outside the graph, so one graph
   //      serves every call of that shape.
   const bool want_graph = ctx->use_graphs && B == 1 && !ready_ev && !ctx->profiling && !ctx->overlap && !two_stage;
-  GraphKey gkey{hd[0].n, iters, with_cheirality, (int)ctx->split_solver | ((int)ctx->early_exit << 1) |
+  // Graphs are keyed on a BUCKET of N (3 significant bits: 8 buckets per octave), not on N itself:
+  // every kernel reads the true point count from the descriptor on the device and only the grid
+  // sizes and the tile length derive from the bucket, so SFMnet's keypoint path — whose N changes
+  // from pair to pair — replays a handful of graphs instead of issuing 15 launches per call.
+  auto bucket_n = [](int n) {
+    if (n <= 1024) return (n + 127) & ~127;
+    int step = 128;
+    while (step * 16 < n) step <<= 1;        // n in (8*step, 16*step]
+    return (n + step - 1) / step * step;
+  };
+  const int grid_n0 = want_graph ? bucket_n(hd[0].n) : hd[0].n;
+  GraphKey gkey{grid_n0, iters, with_cheirality, (int)ctx->split_solver | ((int)ctx->early_exit << 1) |
                                                       ((int)ctx->force_exact << 2) | ((P_out != nullptr) << 3) | ((sets == nullptr) << 4), thr};
   bool build_graph = false;
   if (want_graph) {
@@ -1388,7 +1471,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
     auto front = [&](int c) -> int {
       const int b0 = first[c], nb = first[c + 1] - b0;
       int cmax_pp = 0;
-      for (int b = b0; b < b0 + nb; ++b) cmax_pp = std::max(cmax_pp, (hd[b].n + 1) / 2);
+      for (int b = b0; b < b0 + nb; ++b) cmax_pp = std::max(cmax_pp, ((B == 1 ? grid_n0 : hd[b].n) + 1) / 2);
       const PairDesc* desc = w.desc + b0;
       PairState* state = w.state + b0;
       const size_t so = (size_t)b0 * H;
@@ -1427,7 +1510,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
     auto back = [&](int c) -> int {
       const int b0 = first[c], nb = first[c + 1] - b0;
       int cmax_pp = 0;
-      for (int b = b0; b < b0 + nb; ++b) cmax_pp = std::max(cmax_pp, (hd[b].n + 1) / 2);
+      for (int b = b0; b < b0 + nb; ++b) cmax_pp = std::max(cmax_pp, ((B == 1 ? grid_n0 : hd[b].n) + 1) / 2);
       PairDesc* desc = w.desc + b0;
       PairState* state = w.state + b0;
       Control* ctl = w.ctl + c;
@@ -1552,7 +1635,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
       if (rc_cap == TV5_OK && e_end == cudaSuccess && graph &&
           cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
         cudaGraphDestroy(graph);
-        if (ctx->graphs.size() >= 32) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
+        if (ctx->graphs.size() >= 64) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
         ctx->graphs.push_back({gkey, exec});
         TV5_CUDA(ctx, cudaGraphLaunch(exec, st));
         return submission_leave(ctx, st);
@@ -1978,6 +2061,24 @@ int tv5_plane_sweep(tv5_ctx* ctx, void* stream, const float* ref_feat, const flo
   P.ref = ref_feat; P.tgt = tgt_feat; P.pose = pose; P.K = K; P.Kinv = Kinv; P.cost = cost;
   P.C = C; P.h = h; P.w = w; P.L = nlabel; P.mindepth = mindepth; P.by_depth = by_depth ? 1 : 0;
   plane_sweep<<<dim3((unsigned)((h * w + 31 + 255) / 256), nlabel, B), 256, 0, (cudaStream_t)stream>>>(P);
+  TV5_CUDA(ctx, cudaGetLastError());
+  return TV5_OK;
+}
+
+int tv5_winner_record(tv5_ctx* ctx, void* stream, const double* E, const double* P,
+                      const tv5_result* result, int set_offset, void* record_out) {
+  if (!ctx || !E || !result || !record_out || set_offset < 0) return TV5_ERR_INVALID;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  winner_record<<<1, 32, 0, (cudaStream_t)stream>>>(E, P, result, set_offset, (WinnerRecord*)record_out);
+  TV5_CUDA(ctx, cudaGetLastError());
+  return TV5_OK;
+}
+
+int tv5_winner_pick(tv5_ctx* ctx, void* stream, const void* records, int G, double* E_out,
+                    double* P_out, tv5_result* result_out) {
+  if (!ctx || !records || G < 1 || !E_out || !result_out) return TV5_ERR_INVALID;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  winner_pick<<<1, 32, 0, (cudaStream_t)stream>>>((const WinnerRecord*)records, G, E_out, P_out, result_out);
   TV5_CUDA(ctx, cudaGetLastError());
   return TV5_OK;
 }

@@ -7,9 +7,10 @@ Two ways the path shards:
   to all ranks.
 * hypothesis-sharded (config 4): one large pair, correspondences replicated, rank g scores the
   hypothesis ids [g*H/G, (g+1)*H/G) — i.e. reference threads [g*512/G, (g+1)*512/G) — and the
-  global winner is one MAX all-reduce over a packed (count, ~id) int64 key, followed by a
-  broadcast of the owner's E and P.  The key order reproduces the reference's
-  first-maximum-over-(thread, iteration, root) rule (essential_matrix.cu:252).
+  global winner is taken from ONE all_gather of the ranks' 192-byte (key, E, P) records by a
+  device-side first-maximum over the packed (count, ~id) key; no host synchronisation.  The key
+  order reproduces the reference's first-maximum-over-(thread, iteration, root) rule
+  (essential_matrix.cu:252).
 
 The reference has no counterpart: it runs under torch.nn.DataParallel (main.py:219), whose
 replicas serialise on the extension's blocking call.
@@ -52,44 +53,61 @@ def unpack_key(key):
 
 
 def reduce_winner(count, set_id, root, E, P, group=None):
-    """All ranks call this with their local winner (global hypothesis id).  Returns the global
-    (count, set, root, E, P).  E, P: tensors on the device the backend communicates on."""
+    """Host-level form of the winner reduction (any backend; the gloo tests of the sharding logic
+    use it with CPU tensors).  All ranks call it with their local winner (global set id): ONE
+    all_gather of the 23-double record (key bits, E, P), then the first maximum by key.  Returns the
+    global (count, set, root, E, P).  On CUDA the engine's device-side form is used instead
+    (compute_pose_hypothesis_sharded: tv5_winner_record -> all_gather -> tv5_winner_pick)."""
     dev = E.device
     has = count > 0 and set_id >= 0
     key = torch.tensor([pack_key(count, set_id, root) if has else 0], dtype=torch.int64, device=dev)
-    dist.all_reduce(key, op=dist.ReduceOp.MAX, group=group)
-    gcount, gset, groot = unpack_key(key.item())
+    rec = torch.cat([key.view(torch.float64), E.reshape(-1).double(), P.reshape(-1).double()])
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(rec) for _ in range(world)]
+    dist.all_gather(parts, rec, group=group)
+    allrec = torch.stack(parts)
+    keys = allrec[:, 0].contiguous().view(torch.int64)
+    owner = int(torch.argmax(keys))
+    gcount, gset, groot = unpack_key(int(keys[owner]))
     if gcount == 0:
         return 0, -1, -1, torch.zeros_like(E), torch.zeros_like(P)
-    mine = has and gset == set_id and groot == root and gcount == count
-    # exactly one rank owns the winning id; sum-reduce its payload
-    payload = torch.cat([E.reshape(-1), P.reshape(-1)]) if mine else torch.zeros(
-        E.numel() + P.numel(), dtype=E.dtype, device=dev)
-    dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
-    return gcount, gset, groot, payload[:E.numel()].view_as(E).clone(), payload[E.numel():].view_as(P).clone()
+    n_e = E.numel()
+    return (gcount, gset, groot, allrec[owner, 1:1 + n_e].view_as(E).to(E.dtype).clone(),
+            allrec[owner, 1 + n_e:].view_as(P).to(P.dtype).clone())
+
+
+def local_hypothesis_table(engine, n_points, iters, world, rank, sets=None):
+    """This rank's rows of the [512*iters, 5] minimal-set table (the reference RNG table when sets is
+    None), its first global set id, and the engine's `iters` for that many rows."""
+    t0, tpr, h0 = hypothesis_shard(iters, world, rank)
+    if (tpr * int(iters)) % REF_THREADS:
+        raise ValueError("512*iters/world must be a multiple of 512 (iters divisible by world)")
+    if sets is None:
+        sets = engine.ref_rng_sets(n_points, iters)
+    local = sets.view(REF_THREADS * int(iters), 5)[h0:h0 + tpr * int(iters)].contiguous()
+    # the engine's hypothesis budget is 512 * iters_local: the id layout is kept by cutting the
+    # thread dimension, not the iteration dimension
+    return local, h0, tpr * int(iters) // REF_THREADS
 
 
 def compute_pose_hypothesis_sharded(engine, x1, x2, iters, thr, sets=None, with_cheirality=True,
-                                    group=None):
+                                    group=None, local=None):
     """One large pair on all ranks of `group`; x1/x2 must already be replicated.  `sets` is the
-    full [512*iters, 5] table (or None for the reference RNG table)."""
+    full [512*iters, 5] table (or None for the reference RNG table); `local` = a cached
+    local_hypothesis_table(...) skips the slicing.  Everything is stream-ordered on the device —
+    solve + score of this rank's hypotheses, tv5_winner_record, one all_gather of the 192-byte
+    records over NCCL, tv5_winner_pick — with no host synchronisation; returns a PoseResult whose
+    best_set is the GLOBAL hypothesis id."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    t0, tpr, h0 = hypothesis_shard(iters, world, rank)
-    if sets is None:
-        sets = engine.ref_rng_sets(x1.shape[0], iters)
-    sets = sets.view(REF_THREADS * int(iters), 5)
-    local = sets[h0:h0 + tpr * int(iters)]
-    # the engine's hypothesis budget is 512 * iters_local: keep the id layout by padding the
-    # thread dimension, not the iteration dimension
-    if (tpr * int(iters)) % REF_THREADS:
-        raise ValueError("512*iters/world must be a multiple of 512 (iters divisible by world)")
-    iters_local = tpr * int(iters) // REF_THREADS
-    r = engine.compute_pose(x1, x2, iters_local, thr, sets=local.contiguous(),
-                            with_cheirality=with_cheirality)
-    lset = r.best_set
-    gset = h0 + lset if lset >= 0 else -1
-    return reduce_winner(r.count, gset, r.best_root, r.E, r.P, group=group)
+    if local is None:
+        local = local_hypothesis_table(engine, x1.shape[0], iters, world, rank, sets)
+    table, h0, iters_local = local
+    r = engine.compute_pose(x1, x2, iters_local, thr, sets=table, with_cheirality=with_cheirality)
+    rec = engine.winner_record(r, h0)
+    allrec = torch.empty(world * engine.RECORD_DOUBLES, dtype=torch.float64, device=rec.device)
+    dist.all_gather_into_tensor(allrec, rec, group=group)
+    return engine.winner_pick(allrec)
 
 
 def gather_pair_results(E, P, stats, n_pairs, group=None):

@@ -416,6 +416,31 @@ class Engine:
         _check(self.ctx, rc, "tv5_optimise_host")
         return out.reshape(3, 3)
 
+    # -- hypothesis-sharded single pair: device-side winner record / pick (tv5/dist.py) ---------
+    RECORD_DOUBLES = 24   # TV5_WINNER_RECORD_BYTES / 8
+
+    def winner_record(self, r, set_offset):
+        """192-byte record of a single-pair PoseResult whose set ids start at `set_offset` in the
+        global hypothesis table; float64 [24] on the device (bit container, see include/tv5.h)."""
+        with torch.cuda.device(self.device):
+            rec = torch.empty(self.RECORD_DOUBLES, dtype=torch.float64, device=self.device)
+            rc = self.L.tv5_winner_record(self.ctx, self._stream(), r.E.data_ptr(), r.P.data_ptr(),
+                                          r.stats.data_ptr(), int(set_offset), rec.data_ptr())
+        _check(self.ctx, rc, "tv5_winner_record")
+        return rec
+
+    def winner_pick(self, records):
+        """records: float64 [G*24] (all-gathered) -> PoseResult of the global first maximum."""
+        G = records.numel() // self.RECORD_DOUBLES
+        with torch.cuda.device(self.device):
+            E = torch.empty(3, 3, dtype=torch.float64, device=self.device)
+            P = torch.empty(3, 4, dtype=torch.float64, device=self.device)
+            stats = torch.empty(8, dtype=torch.int32, device=self.device)
+            rc = self.L.tv5_winner_pick(self.ctx, self._stream(), records.data_ptr(), G, E.data_ptr(),
+                                        P.data_ptr(), stats.data_ptr())
+        _check(self.ctx, rc, "tv5_winner_pick")
+        return PoseResult(E, P, stats)
+
     # -- measurement --------------------------------------------------------------------------
     def measure_fp32_peak(self, mode=1):
         v = C.c_double()

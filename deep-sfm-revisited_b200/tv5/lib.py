@@ -119,6 +119,10 @@ def load_library():
     L.tv5_plane_sweep.restype = C.c_int
     L.tv5_plane_sweep.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_float, C.c_int, vp]
+    L.tv5_winner_record.restype = C.c_int
+    L.tv5_winner_record.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
+    L.tv5_winner_pick.restype = C.c_int
+    L.tv5_winner_pick.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
     L.tv5_measure_fp32_peak.restype = C.c_int
     L.tv5_measure_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.tv5_set_force_exact.restype = C.c_int

@@ -258,6 +258,26 @@ int tv5_plane_sweep(tv5_ctx* ctx, void* stream, const float* ref_feat, const flo
                     const float* pose, const float* K, const float* Kinv, int B, int C, int h, int w,
                     int nlabel, float mindepth, int by_depth, float* cost);
 
+/*
+ * Hypothesis-sharded single pair (SURVEY.md section 8(e), configs[3]): every GPU solves and scores
+ * its share of the minimal sets of ONE pair (tv5_compute_pose with the rows [set_offset,
+ * set_offset + H_local) of the index table); the global winner is the reference's first maximum
+ * over (thread, iteration, root) — its host std::max_element over the 512 per-thread results,
+ * essential_matrix.cu:252 — taken across GPUs without a host round trip:
+ *   tv5_winner_record  packs one rank's result into a 192-byte record (device):
+ *                      u64 key = count << 32 | ~(global_set * 16 + root)  (0 when count == 0),
+ *                      E[9], P[12] float64, n_hypotheses, n_candidates, fast_path, pad (int32)
+ *   (the caller all-gathers the G records, e.g. ncclAllGather over NVLink)
+ *   tv5_winner_pick    maximum key over G records -> E_out[9], P_out[12] (may be NULL), result
+ *                      (count, GLOBAL best_set, best_root, summed n_hypotheses / n_candidates).
+ * Both are stream-ordered single-CTA kernels; TV5_WINNER_RECORD_BYTES = 192.
+ */
+#define TV5_WINNER_RECORD_BYTES 192
+int tv5_winner_record(tv5_ctx* ctx, void* stream, const double* E, const double* P,
+                      const tv5_result* result, int set_offset, void* record_out);
+int tv5_winner_pick(tv5_ctx* ctx, void* stream, const void* records, int G, double* E_out,
+                    double* P_out, tv5_result* result_out);
+
 /* Testing/diagnostic switch: on != 0 makes the pose entry points score every hypothesis with the
  * float64 scorer (no float32 guard-band pass).  Results are identical by construction; the
  * tests use this to prove it. */

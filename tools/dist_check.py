@@ -43,7 +43,9 @@ def timed(fn, n=5, warm=2):
     return out, float(t.item())
 
 
-(cnt, gset, groot, E, P), ms_sharded = timed(lambda: tdist.compute_pose_hypothesis_sharded(eng, x1, x2, iters, THR, sets=sets))
+local = tdist.local_hypothesis_table(eng, x1.shape[0], iters, world, rank, sets)
+rs, ms_sharded = timed(lambda: tdist.compute_pose_hypothesis_sharded(eng, x1, x2, iters, THR, local=local), n=20, warm=3)
+cnt, gset, groot, E, P = rs.count, rs.best_set, rs.best_root, rs.E, rs.P
 res = {"world": world, "config4_hypothesis_sharded_ms": ms_sharded, "count": cnt, "set": gset, "root": groot}
 if rank == 0:
     r, ms_single = None, None
