@@ -236,7 +236,9 @@ def run_reference(args):
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config(pairs_per_step, "single GPU, one pair per call (rank 0 only)")}
     tried = []
-    opt = "device code built with -Xcicc -O1: nvcc 12.9's default -O3 build of this kernel faults on sm_100a (DESIGN.md section 7)"
+    opt = ("device code at nvcc's DEFAULT optimisation level, lowered through compute_90 PTX and assembled for sm_100a "
+           "(-gencode arch=compute_90,code=sm_100a): the compute_100a lowering of this kernel faults on B200, and the round-1 "
+           "-Xcicc -O1 build that avoided the fault is 2.1x slower (DESIGN.md section 7)")
     for mode, what in (("ext", "unmodified reference extension sources (oracle/_ref/refext), essential_matrix.computeP per pair; " + opt),
                        ("twin_managed", "reference kernels SetupRandomState + EstimateProjectionMatrix<5> driven by the host "
                                         "flow of essential_matrix.cu:190-280 restated in oracle/ref_twin/ref_kernel.cu (managed memory); " + opt),

@@ -1062,22 +1062,56 @@ using namespace tv5;
     }                                               \
   } while (0)
 
+// ------------------------------------------------------------------------------------------
+// Workspace allocation.  In guard mode (tv5_debug_guard; a testing aid standing in for
+// compute-sanitizer's memcheck / initcheck, which are closed on the B200 pool) every buffer gets a
+// 256-byte zone of 0xA5 on either side, checked by tv5_debug_check_guards, and its payload is filled
+// with a caller-chosen poison byte — at allocation and again on tv5_debug_poison — so that a kernel
+// that reads workspace it did not write produces poison-dependent results (the tests run every
+// scenario under several poisons and require bit-identical outputs).
+// ------------------------------------------------------------------------------------------
+constexpr size_t kGuardBytes = 256;
+static cudaError_t ws_malloc_bytes(tv5_ctx* ctx, void** p, size_t bytes) {
+  if (!ctx->guard) return cudaMalloc(p, bytes);
+  const size_t payload = (bytes + 255) & ~(size_t)255;     // the back zone starts on an aligned address
+  char* base = nullptr;
+  cudaError_t e = cudaMalloc((void**)&base, payload + 2 * kGuardBytes);
+  if (e != cudaSuccess) return e;
+  cudaMemset(base, 0xA5, payload + 2 * kGuardBytes);
+  cudaMemset(base + kGuardBytes, ctx->poison, bytes);
+  ctx->guards.push_back({base + kGuardBytes, base, bytes, payload});
+  *p = base + kGuardBytes;
+  return cudaSuccess;
+}
+template <typename T>
+static cudaError_t ws_malloc(tv5_ctx* ctx, T** p, size_t bytes) { return ws_malloc_bytes(ctx, (void**)p, bytes); }
+static void ws_free(tv5_ctx* ctx, void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < ctx->guards.size(); ++i)
+    if (ctx->guards[i].user == p) {
+      cudaFree(ctx->guards[i].base);
+      ctx->guards.erase(ctx->guards.begin() + i);
+      return;
+    }
+  cudaFree(p);
+}
+
 template <typename T>
 static int grow(tv5_ctx* ctx, T*& p, size_t& cap, size_t need) {
   if (need <= cap && p) return TV5_OK;
-  if (p) cudaFree(p);
+  if (p) ws_free(ctx, p);
   p = nullptr;
   size_t n = std::max(need, cap + cap / 2);
-  if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) { cap = 0; ctx->last_cuda = (int)cudaGetLastError(); return TV5_ERR_NOMEM; }
+  if (ws_malloc(ctx, &p, n * sizeof(T)) != cudaSuccess) { p = nullptr; cap = 0; ctx->last_cuda = (int)cudaGetLastError(); return TV5_ERR_NOMEM; }
   cap = n;
   return TV5_OK;
 }
 template <typename T>
 static int grow_same(tv5_ctx* ctx, T*& p, size_t old_cap, size_t new_cap) {
   if (new_cap == old_cap && p) return TV5_OK;
-  if (p) cudaFree(p);
+  if (p) ws_free(ctx, p);
   p = nullptr;
-  if (cudaMalloc(&p, new_cap * sizeof(T)) != cudaSuccess) { ctx->last_cuda = (int)cudaGetLastError(); return TV5_ERR_NOMEM; }
+  if (ws_malloc(ctx, &p, new_cap * sizeof(T)) != cudaSuccess) { p = nullptr; ctx->last_cuda = (int)cudaGetLastError(); return TV5_ERR_NOMEM; }
   return TV5_OK;
 }
 
@@ -1105,7 +1139,7 @@ static int ensure_workspace_impl(tv5_ctx* ctx, int B, size_t total_pp, size_t to
     if ((rc = grow_same(ctx, w.state, oc, nc))) return rc;
     w.desc_cap = nc;
   }
-  if (!w.ctl && cudaMalloc(&w.ctl, sizeof(Control) * kPipeChunks) != cudaSuccess) return TV5_ERR_NOMEM;
+  if (!w.ctl && ws_malloc(ctx, &w.ctl, sizeof(Control) * kPipeChunks) != cudaSuccess) { w.ctl = nullptr; return TV5_ERR_NOMEM; }
   if ((rc = grow(ctx, w.pp, w.pp_cap, total_pp))) return rc;
   if (total_sets > w.sets_cap || !w.E_list) {
     const size_t oc = w.sets_cap;
@@ -1269,8 +1303,8 @@ int tv5_destroy(tv5_ctx* ctx) {
                   w.out_P, w.out_res, w.polish_jobs, w.polish_partial, w.polish_barrier,
                   w.polish_x, w.polish_E, w.flow_jobs, w.flow_x, w.flow_EP};
   for (void* p : ptrs)
-    if (p) cudaFree(p);
-  if (ctx->rng_u) cudaFree(ctx->rng_u);
+    if (p) ws_free(ctx, p);
+  if (ctx->rng_u) ws_free(ctx, ctx->rng_u);
   if (ctx->last_done) cudaEventDestroy(ctx->last_done);
   if (ctx->copy_stream) {
     cudaStreamDestroy(ctx->copy_stream);
@@ -1311,14 +1345,14 @@ static int ensure_rng_uniform(tv5_ctx* ctx, cudaStream_t st, int iters, const fl
   if (ctx->rng_u) {
     // the old table may be referenced by queued work and by captured graphs
     TV5_CUDA(ctx, cudaDeviceSynchronize());
-    cudaFree(ctx->rng_u);
+    ws_free(ctx, ctx->rng_u);
     ctx->rng_u = nullptr;
     ctx->rng_u_iters = 0;
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     ctx->graphs.clear();
   }
   const int cap = std::max(iters, 8);
-  if (cudaMalloc(&ctx->rng_u, (size_t)TV5_REF_THREADS * cap * 5 * sizeof(float)) != cudaSuccess) {
+  if (ws_malloc(ctx, &ctx->rng_u, (size_t)TV5_REF_THREADS * cap * 5 * sizeof(float)) != cudaSuccess) {
     ctx->rng_u = nullptr;
     ctx->last_cuda = (int)cudaGetLastError();
     return TV5_ERR_NOMEM;
@@ -1941,7 +1975,7 @@ int tv5_optimise_host(tv5_ctx* ctx, void* stream, const double* x1, const double
   Workspace& w = ctx->ws;
   int rc;
   if ((rc = grow(ctx, w.polish_x, w.polish_x_cap, (size_t)std::max(N, 1) * 4))) return rc;
-  if (!w.polish_E && cudaMalloc(&w.polish_E, 9 * sizeof(double)) != cudaSuccess) return TV5_ERR_NOMEM;
+  if (!w.polish_E && ws_malloc(ctx, &w.polish_E, 9 * sizeof(double)) != cudaSuccess) { w.polish_E = nullptr; return TV5_ERR_NOMEM; }
   if (N > 0) {
     TV5_CUDA(ctx, cudaMemcpyAsync(w.polish_x, x1, (size_t)N * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
     TV5_CUDA(ctx, cudaMemcpyAsync(w.polish_x + 2 * (size_t)N, x2, (size_t)N * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -2109,6 +2143,64 @@ int tv5_measure_fp32_peak(tv5_ctx* ctx, int mode, double* tflops_out) {
   cudaFree(sink);
   TV5_CUDA(ctx, cudaGetLastError());
   *tflops_out = best;
+  return TV5_OK;
+}
+
+int tv5_debug_guard(tv5_ctx* ctx, int on, int poison_byte) {
+  if (!ctx) return TV5_ERR_INVALID;
+  // only on a context that has not allocated anything yet: every buffer is then guarded
+  if (ctx->ws.desc || ctx->ws.pp || ctx->ws.E_list || ctx->rng_u || ctx->ws.polish_jobs || ctx->ws.flow_jobs ||
+      ctx->ws.h2d_x || ctx->ws.out_E)
+    return TV5_ERR_INVALID;
+  ctx->guard = on != 0;
+  ctx->poison = poison_byte & 0xff;
+  return TV5_OK;
+}
+
+int tv5_debug_poison(tv5_ctx* ctx, int poison_byte) {
+  if (!ctx || !ctx->guard) return TV5_ERR_INVALID;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  TV5_CUDA(ctx, cudaDeviceSynchronize());
+  ctx->poison = poison_byte & 0xff;
+  for (auto& g : ctx->guards) {
+    if (g.user == (void*)ctx->rng_u) continue;     // the uniform table is written once, by design
+    TV5_CUDA(ctx, cudaMemset(g.user, ctx->poison, g.bytes));
+  }
+  // captured graphs replay the same kernels on the same buffers: nothing to invalidate
+  TV5_CUDA(ctx, cudaDeviceSynchronize());
+  return TV5_OK;
+}
+
+int tv5_debug_check_guards(tv5_ctx* ctx, int64_t* corrupted_bytes_out, int32_t* n_buffers_out) {
+  if (!ctx || !corrupted_bytes_out) return TV5_ERR_INVALID;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  TV5_CUDA(ctx, cudaDeviceSynchronize());
+  int64_t bad = 0;
+  std::vector<unsigned char> h(kGuardBytes);
+  for (auto& g : ctx->guards) {
+    const char* zones[2] = {(const char*)g.base, (const char*)g.user + g.payload};
+    for (const char* z : zones) {
+      TV5_CUDA(ctx, cudaMemcpy(h.data(), z, kGuardBytes, cudaMemcpyDeviceToHost));
+      for (unsigned char c : h) bad += c != 0xA5;
+    }
+    // the slack between the requested size and the 256-byte rounding keeps the zone pattern too
+    if (g.payload > g.bytes) {
+      std::vector<unsigned char> t(g.payload - g.bytes);
+      TV5_CUDA(ctx, cudaMemcpy(t.data(), (const char*)g.user + g.bytes, t.size(), cudaMemcpyDeviceToHost));
+      for (unsigned char c : t) bad += c != 0xA5;
+    }
+  }
+  *corrupted_bytes_out = bad;
+  if (n_buffers_out) *n_buffers_out = (int32_t)ctx->guards.size();
+  return TV5_OK;
+}
+
+int tv5_debug_stray_write(tv5_ctx* ctx, int back) {
+  if (!ctx || !ctx->guard || ctx->guards.empty()) return TV5_ERR_INVALID;
+  TV5_CUDA(ctx, cudaSetDevice(ctx->device));
+  const GuardRec& g = ctx->guards.front();
+  char* at = back ? (char*)g.user + g.payload : (char*)g.user - 1;   // first byte behind / last byte before the payload
+  TV5_CUDA(ctx, cudaMemset(at, 0, 1));
   return TV5_OK;
 }
 

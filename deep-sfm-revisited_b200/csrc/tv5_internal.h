@@ -126,6 +126,7 @@ struct GraphKey {
 };
 struct GraphEntry { GraphKey key; cudaGraphExec_t exec; };
 struct GraphSeen { GraphKey key; int count; };
+struct GuardRec { void* user; void* base; size_t bytes; size_t payload; };   // guard mode: see ws_malloc_bytes
 
 }  // namespace tv5
 
@@ -140,6 +141,9 @@ struct tv5_ctx {
   cudaEvent_t last_done = nullptr;
   bool has_last = false;
   bool force_exact = false;
+  bool guard = false;                   // guard zones + poisoned payloads on every workspace buffer (testing aid)
+  int poison = 0;
+  std::vector<tv5::GuardRec> guards;
   bool profiling = false;
   cudaEvent_t ev[TV5_N_STAGES + 1] = {};
   double stage_ms[TV5_N_STAGES] = {};

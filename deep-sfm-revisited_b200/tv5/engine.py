@@ -441,6 +441,23 @@ class Engine:
         _check(self.ctx, rc, "tv5_winner_pick")
         return PoseResult(E, P, stats)
 
+    # -- testing aid: guard zones + poisoned workspace (include/tv5.h: tv5_debug_guard) ---------
+    def debug_guard(self, poison=0xFF):
+        """Fresh engine only.  Every workspace buffer from now on: guard zones, payload = poison."""
+        _check(self.ctx, self.L.tv5_debug_guard(self.ctx, 1, int(poison)), "tv5_debug_guard")
+
+    def debug_poison(self, poison):
+        _check(self.ctx, self.L.tv5_debug_poison(self.ctx, int(poison)), "tv5_debug_poison")
+
+    def debug_stray_write(self, back=True):
+        _check(self.ctx, self.L.tv5_debug_stray_write(self.ctx, int(bool(back))), "tv5_debug_stray_write")
+
+    def debug_check_guards(self):
+        """(guard bytes overwritten, guarded buffers); synchronises."""
+        bad, n = C.c_int64(), C.c_int32()
+        _check(self.ctx, self.L.tv5_debug_check_guards(self.ctx, C.byref(bad), C.byref(n)), "tv5_debug_check_guards")
+        return bad.value, n.value
+
     # -- measurement --------------------------------------------------------------------------
     def measure_fp32_peak(self, mode=1):
         v = C.c_double()

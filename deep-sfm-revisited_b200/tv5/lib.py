@@ -123,6 +123,14 @@ def load_library():
     L.tv5_winner_record.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
     L.tv5_winner_pick.restype = C.c_int
     L.tv5_winner_pick.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
+    L.tv5_debug_guard.restype = C.c_int
+    L.tv5_debug_guard.argtypes = [vp, C.c_int, C.c_int]
+    L.tv5_debug_poison.restype = C.c_int
+    L.tv5_debug_poison.argtypes = [vp, C.c_int]
+    L.tv5_debug_stray_write.restype = C.c_int
+    L.tv5_debug_stray_write.argtypes = [vp, C.c_int]
+    L.tv5_debug_check_guards.restype = C.c_int
+    L.tv5_debug_check_guards.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     L.tv5_measure_fp32_peak.restype = C.c_int
     L.tv5_measure_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.tv5_set_force_exact.restype = C.c_int

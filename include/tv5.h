@@ -278,6 +278,22 @@ int tv5_winner_record(tv5_ctx* ctx, void* stream, const double* E, const double*
 int tv5_winner_pick(tv5_ctx* ctx, void* stream, const void* records, int G, double* E_out,
                     double* P_out, tv5_result* result_out);
 
+/*
+ * Testing aid (stands in for compute-sanitizer's memcheck / initcheck, which the B200 pool keeps
+ * closed).  tv5_debug_guard must be called on a fresh context, before its first submission: from
+ * then on every workspace buffer is allocated with a 256-byte guard zone on either side and its
+ * payload filled with `poison_byte`.  tv5_debug_poison refills every payload (synchronises);
+ * tv5_debug_check_guards synchronises and counts guard bytes that were overwritten — 0 means no
+ * kernel wrote outside its buffers.  Results must not depend on the poison (tests run 0x00 / 0xFF /
+ * 0x5A and compare bit for bit): no kernel reads workspace that this submission did not write.
+ */
+int tv5_debug_guard(tv5_ctx* ctx, int on, int poison_byte);
+int tv5_debug_poison(tv5_ctx* ctx, int poison_byte);
+int tv5_debug_check_guards(tv5_ctx* ctx, int64_t* corrupted_bytes_out, int32_t* n_buffers_out);
+/* Self-test of the detector: writes one byte just outside the payload of the first guarded buffer
+ * (back != 0: behind it, else in front of it); the next tv5_debug_check_guards must report it. */
+int tv5_debug_stray_write(tv5_ctx* ctx, int back);
+
 /* Testing/diagnostic switch: on != 0 makes the pose entry points score every hypothesis with the
  * float64 scorer (no float32 guard-band pass).  Results are identical by construction; the
  * tests use this to prove it. */
