@@ -231,7 +231,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    pairs_per_step = 2
+    pairs_per_step = 4        # 0.155 s per pair on the reference: 25 steps stay under 20 s
     line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config(pairs_per_step, "single GPU, one pair per call (rank 0 only)")}
@@ -306,10 +306,11 @@ def accuracy_report(eng, dev, n_pairs=64, n_cv2=8):
                 "pairs": len(rc), "rot_diff_max_deg": float(dR.max()), "trans_diff_max_deg": float(dt.max()),
                 "reference_inlier_counts": rc[:8], "inlier_counts_equal": mc == rc,
                 "pairs_with_different_count": diff_cnt, "max_count_difference": int(max(abs(a - b) for a, b in zip(mc, rc))),
-                "pairs_with_different_winner": int(((dR > 1e-6) | (dt > 1e-6)).sum()),
-                "note": "same curand minimal sets; 'different winner' = pose differs by more than 1e-6 degrees, i.e. another "
+                "pairs_with_different_winner": int(((dR > 1e-3) | (dt > 1e-3)).sum()),
+                "note": "same curand minimal sets; 'different winner' = pose differs by more than 1e-3 degrees, i.e. another "
                         "hypothesis won (independent solvers round E differently, which can move a point across the "
-                        "threshold and change the ranking of near-equal hypotheses, SURVEY H2)"}
+                        "threshold and change the ranking of near-equal hypotheses, SURVEY H2); the same hypothesis "
+                        "solved by both differs by < 1e-4 degrees"}
     except Exception as ex:
         out["reference_extension"] = {"unavailable": repr(ex)[:120]}
     try:
@@ -397,53 +398,87 @@ for p in (root, os.path.join(root, "deep-sfm-revisited_b200"), os.path.join(root
 import numpy as np, torch
 import harness, scene
 from tv5 import synth
+torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False   # both backends see the same flow
 ref = harness.load_reference("tv5", overrides={"MIXED_PREC": False})   # fp16 autocast overflows with random-init weights
 sc = scene.make_scene(0)
 H, W = sc["ref"].shape[1:]
 Hp, Wp = int(np.ceil(H / 128) * 128), int(np.ceil(W / 128) * 128)
-net = ref.make_sfmnet(128, seed=0)
-rec = {"flow_ms": [], "pose_stage_ms": [], "computeP_ms": [], "depth_ms": []}
-def wrap(fn, key):
-    def w(*a, **k):
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        r = fn(*a, **k)
-        torch.cuda.synchronize(); rec[key].append((time.perf_counter() - t0) * 1e3)
-        return r
-    return w
-net.flow_estimator.forward = wrap(net.flow_estimator.forward, "flow_ms")
-net.pose_by_ransac = wrap(net.pose_by_ransac, "pose_stage_ms")
-net.depth_estimator.forward = wrap(net.depth_estimator.forward, "depth_ms")
-ref.sfmnet_mod.compute_P_matrix_ransac = wrap(ref.sfmnet_mod.compute_P_matrix_ransac, "computeP_ms")
+
+class FixedFlow(torch.nn.Module):
+    def __init__(self, flow):
+        super().__init__()
+        f = torch.zeros(1, 2, Hp, Wp); f[0, :, :H, :W] = torch.from_numpy(flow)
+        self.register_buffer("flow", f)
+    def forward(self, x):
+        return self.flow.clone(), torch.ones_like(self.flow[:, :1])
+
 pad = (0, Wp - W, 0, Hp - H)
 im0 = torch.nn.functional.pad(torch.from_numpy(sc["ref"])[None].cuda(), pad, "replicate")
 im1 = torch.nn.functional.pad(torch.from_numpy(sc["target"])[None].cuda(), pad, "replicate")
 K = torch.from_numpy(sc["K"])[None]
+orig_cp = ref.sfmnet_mod.compute_P_matrix_ransac
 out = {}
 backends = ["tv5"] + (["refext"] if harness.refext_path() else [])
-for be in backends:
-    ref.use_backend(be)
-    tot = []
-    for r in range(reps + 1):
-        for k in rec: rec[k].clear()
+for variant in ("random_init_dicl", "synthetic_flow"):
+    net = ref.make_sfmnet(128, seed=0)
+    if variant == "synthetic_flow":
+        net.flow_estimator = FixedFlow(sc["flow"]).cuda()
+    rec = {"flow_ms": [], "pose_stage_ms": [], "computeP_ms": [], "depth_ms": []}
+    calls = []
+    def wrap(fn, key):
+        def w(*a, **k):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            r = fn(*a, **k)
+            torch.cuda.synchronize(); rec[key].append((time.perf_counter() - t0) * 1e3)
+            return r
+        return w
+    def cp(c1, c2, *a):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        with torch.no_grad():
-            flow, P, depth, _ = net(im0, im1, K, None, None, False, H, W)     # main.py:533
-        torch.cuda.synchronize(); tot.append((time.perf_counter() - t0) * 1e3)
-    Pn = P[0, 0].double().cpu().numpy()
-    out[be] = {"total_ms": float(np.median(tot[1:])), **{k: float(np.median(v)) for k, v in rec.items()},
-               "P": Pn.tolist(), "depth_finite": bool(torch.isfinite(depth).all()), "depth_mean": float(depth.mean())}
-    out[be]["_d"] = depth.float().cpu()
-if "refext" in out:
-    d0, d1 = out["tv5"].pop("_d"), out["refext"].pop("_d")
-    P0, P1 = np.array(out["tv5"]["P"]), np.array(out["refext"]["P"])
-    out["same_pose"] = {"rot_diff_deg": synth.rotation_error_deg(P0[:, :3], P1[:, :3]),
-                        "trans_diff_deg": synth.translation_error_deg(P0[:, 3], P1[:, 3])}
-    out["depth_max_abs_diff"] = float((d0 - d1).abs().max())
-else:
-    out["tv5"].pop("_d")
+        r = orig_cp(c1, c2, *a)
+        n = int(r[3]); torch.cuda.synchronize(); rec["computeP_ms"].append((time.perf_counter() - t0) * 1e3)
+        calls.append((c1.clone(), c2.clone(), n))
+        return r
+    net.flow_estimator.forward = wrap(net.flow_estimator.forward, "flow_ms")
+    net.pose_by_ransac = wrap(net.pose_by_ransac, "pose_stage_ms")
+    net.depth_estimator.forward = wrap(net.depth_estimator.forward, "depth_ms")
+    ref.sfmnet_mod.compute_P_matrix_ransac = cp
+    res = {}
+    for be in backends:
+        ref.use_backend(be)
+        tot = []
+        for r in range(reps + 1):
+            for k in rec: rec[k].clear()
+            calls.clear()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            with torch.no_grad():
+                flow, P, depth, _ = net(im0, im1, K, None, None, False, H, W)     # main.py:533
+            torch.cuda.synchronize(); tot.append((time.perf_counter() - t0) * 1e3)
+        Pn = P[0, 0].double().cpu().numpy()
+        res[be] = {"total_ms": float(np.median(tot[1:])), **{k: float(np.median(v)) for k, v in rec.items()},
+                   "n_correspondences": int(calls[-1][0].shape[0]), "inliers": calls[-1][2],
+                   "depth_finite": bool(torch.isfinite(depth).all())}
+        res[be]["_P"], res[be]["_d"], res[be]["_c"] = Pn, depth.float().cpu(), calls[-1][:2]
+    if variant == "synthetic_flow":
+        P0 = res["tv5"]["_P"]
+        res["pose_error_vs_ground_truth_deg"] = {"rot": synth.rotation_error_deg(P0[:, :3], sc["R"]),
+                                                 "trans": synth.translation_error_deg(P0[:, 3], sc["t"])}
+    if "refext" in res:
+        a, b = res["tv5"], res["refext"]
+        res["same_inputs"] = bool(torch.equal(a["_c"][0], b["_c"][0]) and torch.equal(a["_c"][1], b["_c"][1]))
+        res["pose_diff_deg"] = {"rot": synth.rotation_error_deg(a["_P"][:, :3], b["_P"][:, :3]),
+                                "trans": synth.translation_error_deg(a["_P"][:, 3], b["_P"][:, 3])}
+        res["depth_max_rel_diff"] = float(((a["_d"] - b["_d"]).abs() / b["_d"].abs().clamp_min(1e-6)).max())
+    for be in backends:
+        for k in ("_P", "_d", "_c"): res[be].pop(k)
+    out[variant] = res
+    ref.sfmnet_mod.compute_P_matrix_ransac = orig_cp
+    del net
+    torch.cuda.empty_cache()
 out["workload"] = ("models/SFMnet.py:95-172 unmodified (staged copy), eval, b=1, nlabel=128, random-init DICL + PSNet "
                    "(cfgs/kitti.yml, MIXED_PREC off), synthetic textured 370x1226 pair padded to 384x1280, cv2 SIFT+FLANN on the host; "
-                   "pose_stage_ms = pose_by_ransac incl. SIFT/FLANN, computeP_ms = compute_P_matrix_ransac alone")
+                   "pose_stage_ms = pose_by_ransac incl. SIFT/FLANN on the CPU, computeP_ms = compute_P_matrix_ransac + int(n) alone; "
+                   "synthetic_flow: the flow network replaced by the scene's flow field (random-init DICL outputs noise, a few "
+                   "dozen inliers and many tied hypotheses, so the pose is only comparable between backends when it is well posed)")
 print("RESULT " + json.dumps(out))
 '''
 
