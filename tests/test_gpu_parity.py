@@ -993,6 +993,79 @@ def test_cuda_graph_replay_equals_plain_launches(engine, std_pair):
     assert torch.equal(small.E, plain_small.E) and small.count == plain_small.count
 
 
+def test_graphs_are_shared_by_a_bucket_of_point_counts(engine, std_pair):
+    """SFMnet's keypoint path calls computeP with a different N on every pair.  Graphs are keyed on a
+    bucket of N (the kernels read the true N from the descriptor; only grids and the tile length
+    come from the bucket): calls with N anywhere inside a bucket, odd and even, at both its ends,
+    replay one graph and must equal plain launches bit for bit — reference-RNG table included,
+    whose scaling depends on N."""
+    sc, x1, x2 = std_pair
+    ns = [3585, 3600, 3999, 4095, 4096, 3777, 3586, 4001]       # one bucket: (3584, 4096]
+    views = [(x1[:n].contiguous(), x2[:n].contiguous()) for n in ns]
+    try:
+        engine.set_graphs(False)
+        plain = [engine.compute_pose(a, b, 5, THR, want_mask=True) for a, b in views]
+        plain_h = [engine.compute_pose(a, b, 2, THR, sets=dev(synth.make_sets(a.shape[0], 1024, 5), torch.int32), want_mask=True)
+                   for a, b in views]
+    finally:
+        engine.set_graphs(True)
+    for rep in range(2):                                         # the third call of the bucket captures, the rest replay
+        got = [engine.compute_pose(a, b, 5, THR, want_mask=True) for a, b in views]
+        got_h = [engine.compute_pose(a, b, 2, THR, sets=dev(synth.make_sets(a.shape[0], 1024, 5), torch.int32), want_mask=True)
+                 for a, b in views]
+        for g, p in zip(got + got_h, plain + plain_h):
+            assert torch.equal(g.E, p.E) and torch.equal(g.P, p.P) and torch.equal(g.mask, p.mask)
+            assert torch.equal(g.stats[:5], p.stats[:5])
+
+
+def test_default_minimal_sets_equal_the_reference_rng_table_for_any_n_and_iters(engine):
+    """sets = NULL draws the reference's table without allocating or synchronising per call: the uniform
+    draws are cached once per context (grown when a call asks for more iterations) and scaled by N on
+    the stream.  Must equal tv5_ref_rng_sets (bit-identical to the reference's curand table,
+    test_reference_rng_table) for every N, in any order of N and iteration counts."""
+    sc = synth.make_pair(20000, seed=12)
+    X1, X2 = dev(sc["x1"]), dev(sc["x2"])
+    for n, iters in ((777, 1), (10000, 8), (5, 3), (20000, 40), (1, 2), (4097, 8), (10000, 2)):
+        a, b = X1[:n].contiguous(), X2[:n].contiguous()
+        r = engine.compute_pose(a, b, iters, THR, want_mask=True)
+        r2 = engine.compute_pose(a, b, iters, THR, sets=engine.ref_rng_sets(n, iters), want_mask=True)
+        assert torch.equal(r.E, r2.E) and torch.equal(r.P, r2.P) and torch.equal(r.mask, r2.mask)
+        assert torch.equal(r.stats[:5], r2.stats[:5])
+    # batch: every pair scales the same draws by its own N
+    ns = [3000, 777, 4096]
+    off = np.r_[0, np.cumsum(ns)]
+    xb1 = torch.cat([X1[:n] for n in ns]).contiguous()
+    xb2 = torch.cat([X2[:n] for n in ns]).contiguous()
+    rb = engine.compute_pose_batch(xb1, xb2, off, 4, THR)
+    for i, n in enumerate(ns):
+        rs = engine.compute_pose(X1[:n].contiguous(), X2[:n].contiguous(), 4, THR, sets=engine.ref_rng_sets(n, 4))
+        assert torch.equal(rb.E[i], rs.E) and int(rb.count[i]) == rs.count and int(rb.best_set[i]) == rs.best_set
+
+
+def test_submissions_on_two_streams_of_one_context_do_not_race(engine, std_pair):
+    """One context = one workspace.  Calls issued on different streams are ordered by an event inside
+    the library (submission_enter / submission_leave), so alternating streams gives the serial results."""
+    sc, x1, x2 = std_pair
+    a1, a2 = x1[:6000].contiguous(), x2[:6000].contiguous()
+    b1, b2 = x1[4000:].contiguous(), x2[4000:].contiguous()
+    sa = dev(synth.make_sets(6000, 2048, 41), torch.int32)
+    sb = dev(synth.make_sets(6000, 2048, 42), torch.int32)
+    ra = engine.compute_pose(a1, a2, 4, THR, sets=sa, want_mask=True)
+    rb = engine.compute_pose(b1, b2, 4, THR, sets=sb, want_mask=True)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for _ in range(12):
+        with torch.cuda.stream(s1):
+            outs.append((engine.compute_pose(a1, a2, 4, THR, sets=sa, want_mask=True), ra))
+        with torch.cuda.stream(s2):
+            outs.append((engine.compute_pose(b1, b2, 4, THR, sets=sb, want_mask=True), rb))
+    torch.cuda.synchronize()
+    for got, want in outs:
+        assert torch.equal(got.E, want.E) and torch.equal(got.P, want.P) and torch.equal(got.mask, want.mask)
+        assert torch.equal(got.stats[:5], want.stats[:5])
+
+
 def test_early_exit_single_large_pair_with_graph_replay(engine):
     """One large pair is staged too (enough work) and, as a single-pair submission, goes through the
     CUDA-graph replay: four identical calls with early exit == the full scoring."""
