@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <new>
 #include <vector>
 
@@ -443,7 +444,9 @@ __global__ void __launch_bounds__(1024) plan_tiles(const PairDesc* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // HPT hypotheses per thread: kHypPerThread for the bulk of the work; 1 (256-slot chunks, more CTAs
 // per SM) for the late early-exit stages, where a pair has only a few hundred hypotheses left.
-template <bool TWO_SIDED, int HPT = kHypPerThread>
+// PARTIAL: tiles of a pair's last, partly filled hypothesis chunk evaluate only the register blocks
+// that hold hypotheses (see below); chosen by the host when a pair has few chunks.
+template <bool TWO_SIDED, int HPT = kHypPerThread, bool PARTIAL = false>
 __global__ void __launch_bounds__(kScoreThreads, (HPT >= kHypPerThread ? TV5_SCORE_MINB : 4))
 score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ state,
              Control* __restrict__ ctl, int B, int H, int pp_per_tile,
@@ -512,18 +515,32 @@ score_bounds(const PairDesc* __restrict__ desc, const PairState* __restrict__ st
     // the very last point pair of an odd-sized image pair holds a duplicated point in lane .y
     const bool odd_tail = (pp0 + npp == npp_all) && (d.n_full & 1);
     const int nfull = odd_tail ? npp - 1 : npp;
+    // A pair's last hypothesis chunk is usually not full (M mod 1024).  PARTIAL: its tiles evaluate only
+    // as many hypotheses per thread as the chunk holds (CTA-uniform K in 1..HPT) instead of carrying
+    // dead register blocks through the loop — 12 % of the evaluations of a 5,500-hypothesis shard
+    // (configs[3] on 8 GPUs: 1.49 -> 1.39 ms).  For an 11,000-hypothesis pair it is 2 %, less than the
+    // extra registers cost the main loop (15.36 -> 15.42 ms per 256 pairs), hence a separate instantiation.
+    const int live_h = min(kScoreThreads * HPT, s.M - hc * (kScoreThreads * HPT));
+    const int k_here = (live_h + kScoreThreads - 1) / kScoreThreads;
+    auto run = [&](auto kc) {
+      constexpr int K = decltype(kc)::value;
 #pragma unroll kScoreUnroll
-    for (int i = 0; i < nfull; ++i) {
-      const PointPair32 p = tile[i];
+      for (int i = 0; i < nfull; ++i) {
+        const PointPair32 p = tile[i];
 #pragma unroll
-      for (int k = 0; k < HPT; ++k) eval_pair<TWO_SIDED>(hr[k], p, bK, nratio, ntwoK, a[k], o[k]);
-    }
-    if (odd_tail) {
-      const PointPair32 p = tile[nfull];
+        for (int k = 0; k < K; ++k) eval_pair<TWO_SIDED>(hr[k], p, bK, nratio, ntwoK, a[k], o[k]);
+      }
+      if (odd_tail) {
+        const PointPair32 p = tile[nfull];
 #pragma unroll
-      for (int k = 0; k < HPT; ++k)
-        eval_pair<TWO_SIDED>(hr[k], p, bK, nratio, ntwoK, a[k], o[k], false);
-    }
+        for (int k = 0; k < K; ++k)
+          eval_pair<TWO_SIDED>(hr[k], p, bK, nratio, ntwoK, a[k], o[k], false);
+      }
+    };
+    if (!PARTIAL || HPT == 1 || k_here == HPT) run(std::integral_constant<int, HPT>());
+    else if (k_here == 1) run(std::integral_constant<int, 1>());
+    else if (k_here == 2) run(std::integral_constant<int, (HPT >= 2 ? 2 : 1)>());
+    else run(std::integral_constant<int, (HPT >= 3 ? 3 : 1)>());
 #pragma unroll
     for (int k = 0; k < HPT; ++k)
       if (live[k]) {
@@ -1608,9 +1625,17 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
       } else {
         plan_tiles<<<1, 1024, 0, s_back>>>(desc, state, ctl, nb, pp_per_tile, kHypChunk);
         if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 4], s_back);
-        if (allow_fast)
-          score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
-                                                                  notin, out);
+        if (allow_fast) {
+          // few hypothesis chunks per pair (a hypothesis shard of one large pair, a small budget): the
+          // partly filled last chunk is a noticeable share -> the PARTIAL instantiation
+          const bool few_chunks = (double)H * (with_cheirality ? 3.0 : 4.5) <= 8.0 * kHypChunk;
+          if (few_chunks)
+            score_bounds<false, kHypPerThread, true><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile,
+                                                                                         w.pp, hyp, notin, out);
+          else
+            score_bounds<false><<<slots, kScoreThreads, 0, s_back>>>(desc, state, ctl, nb, H, pp_per_tile, w.pp, hyp,
+                                                                    notin, out);
+        }
         if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 5], s_back);
       }
       pick_top<<<nb, 1024, 0, s_back>>>(desc, state, H, out, hyp_id, cand, cand_cnt);
