@@ -262,8 +262,11 @@ __global__ void __launch_bounds__(32) solve_sets(const PairDesc* __restrict__ de
 #ifndef TV5_FRONT_ALIAS
 #define TV5_FRONT_ALIAS 1
 #endif
+#ifndef TV5_FRONT_MINB
+#define TV5_FRONT_MINB 12   // <= 168 registers: three warps per SM sub-partition (16,384 registers each)
+#endif
 template <int SPW>
-__global__ void __launch_bounds__(32) solve_front(const PairDesc* __restrict__ desc, int H,
+__global__ void __launch_bounds__(32, TV5_FRONT_MINB) solve_front(const PairDesc* __restrict__ desc, int H,
                                                   double* __restrict__ rec) {
   constexpr int S = SPW + 1;
 #if TV5_FRONT_ALIAS
