@@ -749,6 +749,14 @@ def test_cabi_rejects_bad_arguments_with_error_codes(engine):
     assert L.tv5_plane_sweep(ctx, None, None, None, None, None, None, 1, 1, 4, 4, 1, C.c_float(1.0), 0, None) == -1
     assert L.tv5_flow_to_points(ctx, None, x.data_ptr(), 1, 8, 8, x.data_ptr(), 0, 4, None, None, E.data_ptr(), E.data_ptr()) == -1  # margin eats the image
     assert L.tv5_optimise(ctx, None, x.data_ptr(), x.data_ptr(), -1, None, E.data_ptr(), 1e-4, 1.0, 3, None) == -1
+    rec = torch.zeros(24, dtype=torch.float64, device="cuda")
+    assert L.tv5_winner_record(ctx, None, E.data_ptr(), P.data_ptr(), res.data_ptr(), -1, rec.data_ptr()) == -1   # offset < 0
+    assert L.tv5_winner_record(ctx, None, None, P.data_ptr(), res.data_ptr(), 0, rec.data_ptr()) == -1
+    assert L.tv5_winner_pick(ctx, None, rec.data_ptr(), 0, E.data_ptr(), P.data_ptr(), res.data_ptr()) == -1      # no records
+    assert L.tv5_debug_guard(ctx, 1, 0xFF) == -1    # only on a context that has not allocated anything yet
+    bad, nb = C.c_int64(), C.c_int32()
+    assert L.tv5_debug_poison(ctx, 0) == -1 and L.tv5_debug_stray_write(ctx, 1) == -1     # not in guard mode
+    assert L.tv5_debug_check_guards(ctx, C.byref(bad), C.byref(nb)) == 0 and bad.value == 0 and nb.value == 0
     torch.cuda.synchronize()                        # the context is still healthy
     assert call() == 0
 
