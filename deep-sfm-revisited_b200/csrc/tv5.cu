@@ -296,7 +296,10 @@ static void launch_solve_front(int spw, int H, int nb, cudaStream_t st, const Pa
   else solve_front<32><<<grid, 32, 0, st>>>(desc, H, rec);
 }
 
-__global__ void __launch_bounds__(64) solve_roots(PairState* __restrict__ state, int H,
+#ifndef TV5_ROOTS_MINB
+#define TV5_ROOTS_MINB 6   // 168 registers, no spills: three warps per SM sub-partition
+#endif
+__global__ void __launch_bounds__(64, TV5_ROOTS_MINB) solve_roots(PairState* __restrict__ state, int H,
                                                   double* __restrict__ rec, RootEntry* __restrict__ entries,
                                                   int32_t* __restrict__ n_roots, int32_t* __restrict__ valid_mask) {
   const int h = blockIdx.x * 64 + threadIdx.x;
@@ -317,7 +320,10 @@ __global__ void __launch_bounds__(64) solve_roots(PairState* __restrict__ state,
   }
 }
 
-__global__ void __launch_bounds__(128, 4) solve_poses(const PairDesc* __restrict__ desc, PairState* __restrict__ state,
+#ifndef TV5_POSES_MINB
+#define TV5_POSES_MINB 4
+#endif
+__global__ void __launch_bounds__(128, TV5_POSES_MINB) solve_poses(const PairDesc* __restrict__ desc, PairState* __restrict__ state,
                                                    int H, int with_cheirality, const double* __restrict__ rec,
                                                    const RootEntry* __restrict__ entries,
                                                    double* __restrict__ E_list, double* __restrict__ P_list,
