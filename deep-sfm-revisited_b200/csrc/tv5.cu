@@ -1820,8 +1820,9 @@ int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, i
   if (!ctx || !x1 || !x2 || N < 1 || !sets || H < 1 || !E_list || !n_valid) return TV5_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_workspace(ctx, 1, 1, 1);
+  int rc = ensure_workspace(ctx, 1, 1, ctx->split_solver ? (size_t)H : 1);
   if (rc) return rc;
+  if ((rc = submission_enter(ctx, st))) return rc;
   PairDesc d;
   memset(&d, 0, sizeof(d));
   d.x1 = x1; d.x2 = x2; d.sets = sets; d.n = N; d.n_pre = d.n_full = N;
@@ -1830,8 +1831,6 @@ int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, i
   if (P_list) TV5_CUDA(ctx, cudaMemsetAsync(P_list, 0, (size_t)H * 120 * sizeof(double), st));
   if (ctx->split_solver) {
     Workspace& w = ctx->ws;
-    if ((rc = ensure_workspace(ctx, 1, 1, (size_t)H))) return rc;
-    TV5_CUDA(ctx, cudaMemcpyAsync(w.desc, &d, sizeof(d), cudaMemcpyHostToDevice, st));
     TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState), st));
     const int spw = front_sets_per_warp(H);
     launch_solve_front(spw, H, 1, st, w.desc, w.rec);
@@ -1847,7 +1846,7 @@ int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, i
                                                      n_roots, nullptr, nullptr, nullptr, nullptr);
   }
   TV5_CUDA(ctx, cudaGetLastError());
-  return TV5_OK;
+  return submission_leave(ctx, st);
 }
 
 int tv5_score(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int n_test,
@@ -1879,6 +1878,7 @@ int tv5_score_bounds(tv5_ctx* ctx, void* stream, const double* x1, const double*
   int rc = ensure_workspace(ctx, 1, (size_t)(n_test + 1) / 2, (size_t)H);
   if (rc) return rc;
   Workspace& w = ctx->ws;
+  if ((rc = submission_enter(ctx, st))) return rc;
   PairDesc d;
   memset(&d, 0, sizeof(d));
   d.x1 = x1; d.x2 = x2; d.n = n_test; d.n_pre = d.n_full = n_test; d.pp_off = 0;
@@ -1918,6 +1918,7 @@ int tv5_score_bounds(tv5_ctx* ctx, void* stream, const double* x1, const double*
   PairState hs;
   TV5_CUDA(ctx, cudaMemcpyAsync(&hs, w.state, sizeof(hs), cudaMemcpyDeviceToHost, st));
   TV5_CUDA(ctx, cudaStreamSynchronize(st));
+  if ((rc = submission_leave(ctx, st))) return rc;
   return hs.fast ? TV5_OK : TV5_ERR_INVALID;
 }
 
@@ -1960,6 +1961,7 @@ int tv5_optimise_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, cons
   }
   Workspace& w = ctx->ws;
   int rc;
+  if ((rc = submission_enter(ctx, st))) return rc;
   // jobs go out in waves of at most polish_max_ctas CTAs (a cooperative launch must be co-resident)
   for (int b0 = 0; b0 < B;) {
     const int nb = std::min(B - b0, ctx->polish_max_ctas);
@@ -2001,7 +2003,7 @@ int tv5_optimise_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, cons
     TV5_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)irls_polish, dim3(nb * G), dim3(kPolishThreads), args, 0, st));
     b0 += nb;
   }
-  return TV5_OK;
+  return submission_leave(ctx, st);
 }
 
 int tv5_optimise(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
@@ -2088,11 +2090,12 @@ int tv5_flow_to_points(tv5_ctx* ctx, void* stream, const float* flow, int B, int
     max_n = std::max<int64_t>(max_n, j.n);
   }
   if (max_n == 0) return TV5_OK;
+  if ((rc = submission_enter(ctx, st))) return rc;
   TV5_CUDA(ctx, cudaMemcpyAsync(jobs, hj.data(), sizeof(FlowJob) * B, cudaMemcpyHostToDevice, st));
   flow_points<<<dim3((unsigned)((max_n + 255) / 256), B), 256, 0, st>>>(jobs, H, W, mode, (double2*)x1_out,
                                                                        (double2*)x2_out);
   TV5_CUDA(ctx, cudaGetLastError());
-  return TV5_OK;
+  return submission_leave(ctx, st);
 }
 
 int tv5_pose_from_flow(tv5_ctx* ctx, void* stream, const float* flow, int B, int H, int W,

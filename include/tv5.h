@@ -50,7 +50,11 @@ typedef struct tv5_ctx tv5_ctx;
  * reference-RNG index tables.  No global state — replaces the reference's module-level
  * __constant__ parameters (kernel_functions.cu:16-20) and its per-call cudaMallocManaged /
  * cudaFree (essential_matrix.cu:222-274).  A context may be used from one host thread at a
- * time; different contexts are independent. */
+ * time; different contexts are independent.  One context owns one workspace: submissions made on
+ * different streams are ordered inside the library (the later one first waits for the completion
+ * event of the earlier one), so they never overlap on the device; use one context per stream for
+ * concurrency.  If growing the workspace fails (TV5_ERR_NOMEM) the context stays usable: the next
+ * call reallocates every buffer. */
 int tv5_create(int device, tv5_ctx** out);
 int tv5_destroy(tv5_ctx* ctx);
 const char* tv5_strerror(int code);
