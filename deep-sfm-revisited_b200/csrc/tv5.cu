@@ -1342,6 +1342,9 @@ int tv5_destroy(tv5_ctx* ctx) {
   for (auto e : ctx->prof_ev) cudaEventDestroy(e);
   for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
+  if (ctx->cap_stream2) cudaStreamDestroy(ctx->cap_stream2);
+  if (ctx->cap_fork) cudaEventDestroy(ctx->cap_fork);
+  if (ctx->cap_join) cudaEventDestroy(ctx->cap_join);
   if (ctx->front_stream) {
     cudaStreamDestroy(ctx->front_stream);
     cudaStreamDestroy(ctx->back_stream);
@@ -1494,6 +1497,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
     }
   }
   cudaStream_t sx = st;   // the stream the work is enqueued on (the capture stream while a graph is built)
+  bool capturing = false;
   auto enqueue_all = [&]() -> int {
   TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState) * B, sx));
     const int allow_fast = (two_stage || ctx->force_exact) ? 0 : 1;
@@ -1541,9 +1545,21 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
         for (int j = (c == 0 ? 0 : k); j <= k; ++j) TV5_CUDA(ctx, cudaStreamWaitEvent(s_front, ready_ev[j], 0));
       }
       if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 0], s_front);
-      prep_norms<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_front>>>(desc, state);
-      band_consts<<<(nb + 127) / 128, 128, 0, s_front>>>(desc, state, nb, thr, allow_fast);
-      if (allow_fast) prep_points<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_front>>>(desc, state, w.pp);
+      // While a single-pair graph is being captured the point preparation becomes a branch of its
+      // own: nothing before solve_poses (which needs the pair's scale from band_consts) depends on
+      // it, so in the replayed graph it runs next to the table scaling, solve_front and solve_roots
+      // instead of in front of them (about 10 us of a 170 us call).
+      const bool fork = capturing && ctx->split_solver && ctx->cap_stream2;
+      cudaStream_t s_prep = s_front;
+      if (fork) {
+        TV5_CUDA(ctx, cudaEventRecord(ctx->cap_fork, s_front));
+        TV5_CUDA(ctx, cudaStreamWaitEvent(ctx->cap_stream2, ctx->cap_fork, 0));
+        s_prep = ctx->cap_stream2;
+      }
+      prep_norms<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_prep>>>(desc, state);
+      band_consts<<<(nb + 127) / 128, 128, 0, s_prep>>>(desc, state, nb, thr, allow_fast);
+      if (allow_fast) prep_points<<<dim3((cmax_pp + 255) / 256, nb), 256, 0, s_prep>>>(desc, state, w.pp);
+      if (fork) TV5_CUDA(ctx, cudaEventRecord(ctx->cap_join, s_prep));
       if (prof) cudaEventRecord(ctx->prof_ev[c * kProfPerChunk + 1], s_front);
       if (rng_u) rng_scale_sets<<<dim3((H * 5 + 255) / 256, nb), 256, 0, s_front>>>(desc, H, iters, rng_u,
                                                                                    w.rng_sets + so * 5);
@@ -1553,6 +1569,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
         solve_roots<<<dim3((H + 63) / 64, nb), 64, 0, s_front>>>(state, H, w.rec + so * kRecDoubles,
                                                                  (RootEntry*)w.entries + so * 10, w.n_roots + so,
                                                                  w.n_valid + so);
+        if (fork) TV5_CUDA(ctx, cudaStreamWaitEvent(s_front, ctx->cap_join, 0));
         solve_poses<<<dim3((H * 10 + 127) / 128, nb), 128, 0, s_front>>>(
             desc, state, H, with_cheirality, w.rec + so * kRecDoubles, (const RootEntry*)w.entries + so * 10,
             w.E_list + so * 90, with_cheirality ? w.P_list + so * 120 : nullptr, w.n_valid + so, w.hyp + so * 10,
@@ -1695,8 +1712,16 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
       cudaGetLastError();
       ctx->use_graphs = false;
     } else if (cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      if (!ctx->cap_stream2 && (cudaStreamCreateWithFlags(&ctx->cap_stream2, cudaStreamNonBlocking) != cudaSuccess ||
+                                cudaEventCreateWithFlags(&ctx->cap_fork, cudaEventDisableTiming) != cudaSuccess ||
+                                cudaEventCreateWithFlags(&ctx->cap_join, cudaEventDisableTiming) != cudaSuccess)) {
+        cudaGetLastError();
+        ctx->cap_stream2 = nullptr;   // no fork: the graph is captured as one chain
+      }
       sx = ctx->cap_stream;
+      capturing = true;
       const int rc_cap = enqueue_all();
+      capturing = false;
       cudaGraph_t graph = nullptr;
       const cudaError_t e_end = cudaStreamEndCapture(ctx->cap_stream, &graph);
       cudaGraphExec_t exec = nullptr;

@@ -158,6 +158,8 @@ struct tv5_ctx {
   std::vector<tv5::GraphEntry> graphs;
   std::vector<tv5::GraphSeen> graph_seen;   // shapes seen so far; captured on the third occurrence
   cudaStream_t cap_stream = nullptr;
+  cudaStream_t cap_stream2 = nullptr;   // second branch while capturing (point preparation next to the solver front)
+  cudaEvent_t cap_fork = nullptr, cap_join = nullptr;
   bool early_exit = false;              // staged scoring with exact hypothesis pruning (opt-in)
   int early_stages = 3;                 // ... stage boundaries as fractions of a pair's points
   float early_frac[tv5::kEarlyMaxStages + 1] = {0.0f, 0.30f, 0.52f, 1.0f};
