@@ -128,3 +128,18 @@ def test_guard_zones_do_detect_a_stray_write(engine):
         assert g.debug_check_guards()[0] == 2
     finally:
         g.close()
+
+
+def test_differential_fuzz_of_the_pose_entry_points():
+    """tools/fuzz_paths.py: random shapes, budgets, thresholds and modes (early exit, graph replay, solver form,
+    host-supplied vs reference minimal sets), non-finite / degenerate / huge coordinates — the float32 guard-band
+    route equals the all-float64 route bit for bit, batches equal their pairs solved one by one, and the guard zones
+    of the fuzzed context stay intact."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pr = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_paths.py"), "250", "7"], capture_output=True,
+                        text=True, timeout=600)
+    assert pr.returncode == 0, (pr.stdout + pr.stderr)[-800:]
+    assert "fuzz ok" in pr.stdout
