@@ -1199,8 +1199,11 @@ static int ensure_workspace_impl(tv5_ctx* ctx, int B, size_t total_pp, size_t to
   return TV5_OK;
 }
 
-// fewer sets per warp for small submissions (shorter critical path, more warps), 32 for throughput
-static int front_sets_per_warp(int64_t total_sets) {
+// Sets per warp of solve_front: fewer for small submissions (shorter critical path, more warps), 32 for
+// throughput.  Measured round 2 (tools/batch_sweep.py, solver ms at 2 / 4 / 8 / 16 / 32 pairs of 4,096 sets):
+// this rule 0.081 / 0.101 / 0.148 / 0.272 / 0.453; always 32: 0.094 / 0.105 / 0.148 / 0.272 / 0.453; a rule
+// that minimises (waves x per-warp cost) picked 16 up to 32 pairs and lost: 0.183 / 0.316 / 0.487 at 8 / 16 / 32.
+static int front_sets_per_warp(int64_t total_sets, int /*sm_count*/) {
   if (const char* e = getenv("TV5_FRONT_SPW")) return atoi(e) == 8 ? 8 : (atoi(e) == 16 ? 16 : 32);   // dev knob
   return total_sets <= 8192 ? 8 : (total_sets <= 16384 ? 16 : 32);
 }
@@ -1564,7 +1567,7 @@ static int pose_batch_impl(tv5_ctx* ctx, void* stream, int B, const double* x1, 
       if (rng_u) rng_scale_sets<<<dim3((H * 5 + 255) / 256, nb), 256, 0, s_front>>>(desc, H, iters, rng_u,
                                                                                    w.rng_sets + so * 5);
       if (ctx->split_solver) {
-        const int spw = front_sets_per_warp((int64_t)nb * H);
+        const int spw = front_sets_per_warp((int64_t)nb * H, ctx->sm_count);
         launch_solve_front(spw, H, nb, s_front, desc, w.rec + so * kRecDoubles);
         solve_roots<<<dim3((H + 63) / 64, nb), 64, 0, s_front>>>(state, H, w.rec + so * kRecDoubles,
                                                                  (RootEntry*)w.entries + so * 10, w.n_roots + so,
@@ -1857,7 +1860,7 @@ int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, i
   if (ctx->split_solver) {
     Workspace& w = ctx->ws;
     TV5_CUDA(ctx, cudaMemsetAsync(w.state, 0, sizeof(PairState), st));
-    const int spw = front_sets_per_warp(H);
+    const int spw = front_sets_per_warp(H, ctx->sm_count);
     launch_solve_front(spw, H, 1, st, w.desc, w.rec);
     solve_roots<<<dim3((H + 63) / 64, 1), 64, 0, st>>>(w.state, H, w.rec, (RootEntry*)w.entries, n_roots, n_valid);
     solve_poses<<<dim3((H * 10 + 127) / 128, 1), 128, 0, st>>>(w.desc, w.state, H, with_cheirality, w.rec,
