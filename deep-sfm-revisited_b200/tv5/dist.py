@@ -110,28 +110,35 @@ def compute_pose_hypothesis_sharded(engine, x1, x2, iters, thr, sets=None, with_
     return engine.winner_pick(allrec)
 
 
+_REC = 25   # doubles per pair: E 9 + P 12 + the eight int32 of tv5_result as 4 doubles (bit container)
+
+
 def gather_pair_results(E, P, stats, n_pairs, group=None):
-    """all_gather of pair-sharded results into [n_pairs, ...] tensors (ragged shards padded)."""
+    """all_gather of pair-sharded results into [n_pairs, ...] tensors: ONE collective on a packed
+    [pairs, 25] float64 record (E, P and the tv5_result bits), ragged shards padded to the largest."""
     world = dist.get_world_size(group)
-    per = max(pair_shard(n_pairs, world, r)[1] - pair_shard(n_pairs, world, r)[0] for r in range(world))
+    spans = [pair_shard(n_pairs, world, r) for r in range(world)]
+    per = max(b - a for a, b in spans)
     dev = E.device
-
-    def pad(t, width):
-        out = torch.zeros((per, width), dtype=t.dtype, device=dev)
-        out[: t.shape[0]] = t.reshape(t.shape[0], width)
-        return out
-
-    bufs = []
-    for t, width in ((E, 9), (P, 12), (stats, 8)):
-        mine = pad(t, width)
-        parts = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(parts, mine, group=group)
-        keep = []
-        for r in range(world):
-            a, b = pair_shard(n_pairs, world, r)
-            keep.append(parts[r][: b - a])
-        bufs.append(torch.cat(keep, 0))
-    return bufs[0].view(n_pairs, 3, 3), bufs[1].view(n_pairs, 3, 4), bufs[2]
+    n = E.shape[0]
+    rec = torch.zeros((per, _REC), dtype=torch.float64, device=dev)
+    rec[:n, :9] = E.reshape(n, 9)
+    rec[:n, 9:21] = P.reshape(n, 12)
+    rec[:n, 21:] = stats.reshape(n, 8).contiguous().view(torch.float64)
+    out = torch.empty((world * per, _REC), dtype=torch.float64, device=dev)
+    try:
+        dist.all_gather_into_tensor(out, rec, group=group)
+    except (RuntimeError, NotImplementedError):      # a backend without the flat form
+        parts = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(parts, rec, group=group)
+        out = torch.cat(parts, 0)
+    if per * world != n_pairs:                       # ragged: drop the padding rows
+        keep = torch.cat([torch.arange(r * per, r * per + (b - a), device=dev) for r, (a, b) in enumerate(spans)])
+        out = out.index_select(0, keep)
+    Eg = out[:, :9].reshape(n_pairs, 3, 3)
+    Pg = out[:, 9:21].reshape(n_pairs, 3, 4)
+    sg = out[:, 21:].contiguous().view(torch.int32).reshape(n_pairs, 8)
+    return Eg, Pg, sg
 
 
 def shard_offsets(offsets, start, stop):
