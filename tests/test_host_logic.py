@@ -51,6 +51,26 @@ def test_hypothesis_shard_and_key_order():
     assert off.tolist() == [0, 15, 30] and (a, b) == (10, 40)
 
 
+def test_local_hypothesis_table_cuts_the_thread_dimension():
+    """Rank g of G owns reference threads [g*512/G, (g+1)*512/G), i.e. a contiguous range of hypothesis ids
+    h = thread*iters + it: the concatenation of the ranks' tables is the full table, in id order."""
+    iters = 32
+    full = torch.arange(512 * iters * 5, dtype=torch.int32).view(512 * iters, 5)
+    for world in (1, 2, 4, 8):
+        rows = []
+        for rank in range(world):
+            table, h0, iters_local = tdist.local_hypothesis_table(None, 1000, iters, world, rank, full)
+            assert table.shape == (512 * iters // world, 5) and table.is_contiguous()
+            assert h0 == rank * 512 * iters // world and iters_local * 512 == table.shape[0]
+            assert int(table[0, 0]) == h0 * 5
+            rows.append(table)
+        assert torch.equal(torch.cat(rows), full)
+    with pytest.raises(ValueError):
+        tdist.local_hypothesis_table(None, 1000, 3, 8, 0, torch.zeros(512 * 3, 5, dtype=torch.int32))   # 3 iterations do not split 8 ways
+    with pytest.raises(ValueError):
+        tdist.hypothesis_shard(8, 3, 0)                                                                  # 512 % 3
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
