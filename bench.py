@@ -731,6 +731,7 @@ def run_ours(args):
         if B == PAIRS_PER_GPU:
             roof["traffic"] = tr["dram_bytes_per_launch"]
             roof["traffic_source"] = tr["source"]
+            roof["traffic_commit"] = tr.get("commit")
             # what the kernel must read once: packed point pairs + hypothesis records + counters
             roof["algorithmic_bytes_per_launch"] = float(B * ((N_CORR + 1) // 2) * 48 + M_total * (48 + 8))
     except Exception:
