@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TV5_VERSION 100 /* 0.1.0 */
+#define TV5_VERSION 110 /* 0.1.1: winner record / pick, debug guard entry points, N-bucketed graphs */
 
 /* error codes */
 #define TV5_OK 0
