@@ -24,6 +24,10 @@
 #include <math.h>
 #include <stdint.h>
 
+#ifndef TV5_ISOLATE_TOP_IN_REGS
+#define TV5_ISOLATE_TOP_IN_REGS 1
+#endif
+
 namespace tv5 {
 
 #ifdef TV5_SOLVE_PROFILE
@@ -682,7 +686,56 @@ __device__ inline int isolate_roots_deg10(const double (&poly)[11], FastChain& s
   const int vlo0 = fast_changes(s, -bound), vhi0 = fast_changes(s, bound);
   if (vlo0 - vhi0 <= 0) return 0;
 
-  // flat isolation loop: every trip performs exactly one Sturm count
+  // flat isolation loop: every trip performs at most one Sturm count.  The interval being worked on
+  // (the top of the stack) lives in registers; only the right halves set aside by a split go through
+  // the (local-memory) stack, so a trip that merely narrows an interval touches no memory at all
+  // (the loop used to reload and store its four stack fields on every trip: 44 % of solve_roots'
+  // stall samples were long-scoreboard waits on those local accesses).  Same trips, same order.
+#if TV5_ISOLATE_TOP_IN_REGS
+  double slo[11], shi[11];
+  int svlo[11], svhi[11];
+  int sp = 0, ni = 0;                                   // sp: intervals waiting on the stack
+  double lo = -bound, hi = bound;
+  int vlo = vlo0, vhi = vhi0;
+  for (int trip = 0; trip < 400; ++trip) {
+#ifdef TV5_SOLVE_COUNT
+    atomicAdd(&g_solve_prof[8], 1ull);
+#endif
+    const int n = vlo - vhi;
+    bool pop = false;
+    if (n <= 0) {
+      pop = true;
+    } else if (n == 1) {
+      if (ni < 10) { ilo[ni] = lo; ihi[ni] = hi; ivlo[ni] = vlo; ++ni; }
+      pop = true;
+    } else {
+      const double mid = 0.5 * (lo + hi);
+      if (!(mid > lo && mid < hi) || ni + n > 10) {  // unresolvable cluster: report at the midpoint
+        for (int i = 0; i < n && ni < 10; ++i) { ilo[ni] = mid; ihi[ni] = mid; ivlo[ni] = -1; ++ni; }
+        pop = true;
+      } else {
+#ifdef TV5_SOLVE_COUNT
+        atomicAdd(&g_solve_prof[9], 1ull);
+#endif
+        const int vmid = fast_changes(s, mid);
+        const int n1 = vlo - vmid, n2 = vmid - vhi;
+        if (n1 > 0 && n2 > 0 && sp < 11) {   // split: right half set aside, left half next
+          slo[sp] = mid; shi[sp] = hi; svlo[sp] = vmid; svhi[sp] = vhi; ++sp;
+          hi = mid; vhi = vmid;
+        } else if (n1 == 0) {
+          lo = mid; vlo = vmid;
+        } else {
+          hi = mid; vhi = vmid;
+        }
+      }
+    }
+    if (pop) {
+      if (sp == 0) break;
+      --sp;
+      lo = slo[sp]; hi = shi[sp]; vlo = svlo[sp]; vhi = svhi[sp];
+    }
+  }
+#else
   double slo[12], shi[12];
   int svlo[12], svhi[12];
   int sp = 1, ni = 0;
@@ -720,6 +773,7 @@ __device__ inline int isolate_roots_deg10(const double (&poly)[11], FastChain& s
       shi[t] = mid; svhi[t] = vmid;
     }
   }
+#endif
   TV5_RTICK(7);
   return ni;
 }

@@ -105,8 +105,10 @@ __device__ __forceinline__ void solve_front_warp(bool valid, const Gather& gathe
 }
 
 // ---- solve_roots: one thread per set ----------------------------------------------------------
-// Returns the number of real roots; entries[0..n) receive the isolated roots in ascending order.
-__device__ inline int solve_roots_set(double* __restrict__ rec, RootEntry (&ent)[10]) {
+// Returns the number of real roots n; alloc(n) (called once, when n > 0) returns where the set's n
+// root entries go — they are written there directly, in ascending order, with `set` filled in.
+template <typename Alloc>
+__device__ inline int solve_roots_set(double* __restrict__ rec, int set, Alloc alloc) {
   if (!(rec[kRecOk] == 1.0)) return 0;
   double poly[11];
 #pragma unroll
@@ -118,19 +120,32 @@ __device__ inline int solve_roots_set(double* __restrict__ rec, RootEntry (&ent)
   if (ni < 0) {  // generic chain (rare): roots come back refined, in w
     double roots[10];
     ni = real_roots_deg10_generic(poly, roots);
-    for (int i = 0; i < ni; ++i) { ent[i].lo = ent[i].hi = roots[i]; ent[i].r_exact = i | (1 << 8); }
+    if (ni > 0) {
+      RootEntry* __restrict__ dst = alloc(ni);
+      for (int i = 0; i < ni; ++i) {
+        RootEntry e;
+        e.lo = e.hi = roots[i];
+        e.set = set;
+        e.r_exact = i | (1 << 8);
+        dst[i] = e;
+      }
+    }
     rec[kRecBack] = 1.0;
     return ni;
   }
-  for (int i = 0; i < ni; ++i) {
-    double lo = ilo[i], hi = ihi[i], flo = 0.0;
-    int exact = 1;
-    if (ivlo[i] >= 0) exact = prepare_bracket(s, lo, hi, ivlo[i], flo);
-    ent[i].lo = lo;
-    ent[i].hi = exact ? lo : hi;
-    ent[i].r_exact = i | (exact << 8);
-  }
   if (ni > 0) {
+    RootEntry* __restrict__ dst = alloc(ni);
+    for (int i = 0; i < ni; ++i) {
+      double lo = ilo[i], hi = ihi[i], flo = 0.0;
+      int exact = 1;
+      if (ivlo[i] >= 0) exact = prepare_bracket(s, lo, hi, ivlo[i], flo);
+      RootEntry e;
+      e.lo = lo;
+      e.hi = exact ? lo : hi;
+      e.set = set;
+      e.r_exact = i | (exact << 8);
+      dst[i] = e;
+    }
 #pragma unroll
     for (int i = 0; i < 11; ++i) rec[kRecPoly + i] = s.c[0][i];
     rec[kRecBack] = back;

@@ -306,18 +306,12 @@ __global__ void __launch_bounds__(64, TV5_ROOTS_MINB) solve_roots(PairState* __r
   if (h >= H) return;
   const int b = blockIdx.y;
   const size_t s = (size_t)b * H + h;
-  RootEntry ent[10];
-  const int n = solve_roots_set(rec + s * kRecDoubles, ent);
+  // the set's entries go straight to their slots (reserved by one atomicAdd once the count is known)
+  const int n = solve_roots_set(rec + s * kRecDoubles, h, [&](int cnt) {
+    return entries + (size_t)b * H * 10 + atomicAdd(&state[b].n_entries, cnt);
+  });
   if (n_roots) n_roots[s] = n;
   valid_mask[s] = 0;
-  if (n > 0) {
-    const int base = atomicAdd(&state[b].n_entries, n);
-    RootEntry* __restrict__ dst = entries + (size_t)b * H * 10 + base;
-    for (int i = 0; i < n; ++i) {
-      ent[i].set = h;
-      dst[i] = ent[i];
-    }
-  }
 }
 
 #ifndef TV5_POSES_MINB
