@@ -19,6 +19,10 @@
 #pragma once
 #include "solve5_coop.cuh"
 
+#ifndef TV5_POSES_PREFETCH
+#define TV5_POSES_PREFETCH 1
+#endif
+
 namespace tv5 {
 
 constexpr int kRecDoubles = 96;     // record per set
@@ -159,6 +163,12 @@ template <typename Gather>
 __device__ inline bool solve_pose_root(const double* __restrict__ rec, const RootEntry& en, bool with_cheirality,
                                        const Gather& gather, double (&E)[9], double (&P)[12]) {
   const double2* __restrict__ rec2 = reinterpret_cast<const double2*>(rec);
+#if TV5_POSES_PREFETCH
+  // the basis and the hidden-variable matrix (first five 128-byte lines of the record) are needed only
+  // after the Newton refinement: ask for them now, the refinement runs while they arrive
+#pragma unroll
+  for (int l = 0; l < 5; ++l) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 16 * l));
+#endif
   double w;
   if (en.r_exact >> 8) {
     w = en.lo * rec[kRecBack];
