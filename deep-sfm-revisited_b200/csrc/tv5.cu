@@ -1073,6 +1073,18 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* sink, int iters, 
 // ==========================================================================================
 using namespace tv5;
 
+// Every entry point that touches the context's workspace or settings holds the context's (recursive)
+// mutex for the duration of the call: two host threads sharing one context are serialised instead of
+// racing on the workspace (entry points call each other, hence recursive; a null context locks nothing).
+struct CtxLock {
+  std::recursive_mutex* m;
+  explicit CtxLock(tv5_ctx* c) : m(c ? &c->mu : nullptr) { if (m) m->lock(); }
+  ~CtxLock() { if (m) m->unlock(); }
+  CtxLock(const CtxLock&) = delete;
+  CtxLock& operator=(const CtxLock&) = delete;
+};
+#define TV5_LOCK(ctx) CtxLock lock__(ctx)
+
 #define TV5_CUDA(ctx, call)                         \
   do {                                              \
     cudaError_t e__ = (call);                       \
@@ -1357,6 +1369,7 @@ int tv5_last_cuda_error(const tv5_ctx* ctx) { return ctx ? ctx->last_cuda : 0; }
 int tv5_device_sm_count(const tv5_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 int tv5_ref_rng_sets(tv5_ctx* ctx, void* stream, int N, int iters, int32_t* sets_out) {
+  TV5_LOCK(ctx);
   if (!ctx || N < 1 || iters < 1 || !sets_out) return TV5_ERR_INVALID;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
   ref_rng_kernel<<<8, 64, 0, (cudaStream_t)stream>>>(N, iters, sets_out);
@@ -1747,6 +1760,7 @@ int tv5_compute_pose_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, 
                            const int64_t* pt_offsets, const int32_t* sets, int iters, int n_pre,
                            int n_full, double thr, int with_cheirality, double* E_out,
                            double* P_out, tv5_result* result, uint8_t* mask_out) {
+  TV5_LOCK(ctx);
   return pose_batch_impl(ctx, stream, B, x1, x2, pt_offsets, sets, iters, n_pre, n_full, thr, with_cheirality,
                          E_out, P_out, result, mask_out, nullptr, nullptr, 0);
 }
@@ -1765,6 +1779,7 @@ int tv5_compute_pose_batch_host(tv5_ctx* ctx, void* stream, int B, const double*
                                 const double* x2, const int64_t* pt_offsets, const int32_t* sets,
                                 int iters, int n_pre, int n_full, double thr, int with_cheirality,
                                 double* E_out, double* P_out, tv5_result* result) {
+  TV5_LOCK(ctx);
   if (!ctx || B < 1 || !x1 || !x2 || !pt_offsets || !E_out || !result || iters < 1) return TV5_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1839,6 +1854,7 @@ int tv5_compute_pose_batch_host(tv5_ctx* ctx, void* stream, int B, const double*
 int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
                const int32_t* sets, int H, int with_cheirality, double* E_list, double* P_list,
                int32_t* n_roots, int32_t* n_valid) {
+  TV5_LOCK(ctx);
   if (!ctx || !x1 || !x2 || N < 1 || !sets || H < 1 || !E_list || !n_valid) return TV5_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1873,6 +1889,7 @@ int tv5_solve5(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, i
 
 int tv5_score(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int n_test,
               const double* E_list, int M, double thr, int32_t* counts, uint32_t* masks) {
+  TV5_LOCK(ctx);
   if (!ctx || n_test < 0 || M < 0) return TV5_ERR_INVALID;
   if (M == 0) return TV5_OK;
   if (!E_list || !counts || (n_test > 0 && (!x1 || !x2))) return TV5_ERR_INVALID;
@@ -1892,6 +1909,7 @@ int tv5_score(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, in
 
 int tv5_score_bounds(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int n_test,
                      const double* E_list, int M, double thr, int32_t* lo, int32_t* hi) {
+  TV5_LOCK(ctx);
   if (!ctx || !x1 || !x2 || n_test < 1 || !E_list || M < 1 || !lo || !hi || !(thr > 0.0)) return TV5_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1961,6 +1979,7 @@ int tv5_decompose_uv(const double* E, double* U, double* V) {
 
 int tv5_decompose_batch(tv5_ctx* ctx, void* stream, const double* E, int B, double* angles, double* U,
                         double* V) {
+  TV5_LOCK(ctx);
   if (!ctx || !E || B < 0 || (!angles && !U && !V)) return TV5_ERR_INVALID;
   if (B == 0) return TV5_OK;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1972,6 +1991,7 @@ int tv5_decompose_batch(tv5_ctx* ctx, void* stream, const double* E, int B, doub
 int tv5_optimise_batch(tv5_ctx* ctx, void* stream, int B, const double* x1, const double* x2,
                        const int64_t* pt_offsets, const uint8_t* mask, double* E_io, double delta,
                        double alpha, int max_reps, int32_t* iters_out) {
+  TV5_LOCK(ctx);
   if (!ctx || B < 1 || !pt_offsets || !E_io || max_reps < 0) return TV5_ERR_INVALID;
   max_reps = std::min(max_reps, 1000000);   // keeps the monotonic barrier counter (reps x CTAs) inside 32 bits
   cudaStream_t st = (cudaStream_t)stream;
@@ -2038,6 +2058,7 @@ int tv5_optimise(tv5_ctx* ctx, void* stream, const double* x1, const double* x2,
 
 int tv5_optimise_host(tv5_ctx* ctx, void* stream, const double* x1, const double* x2, int N,
                       const double* E_init, double delta, double alpha, int max_reps, double* E_out) {
+  TV5_LOCK(ctx);
   if (!ctx || N < 0 || !E_init || !E_out || (N > 0 && (!x1 || !x2))) return TV5_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -2080,6 +2101,7 @@ static int flow_offsets(int B, int H, int W, int mode, int margin, const int64_t
 int tv5_flow_to_points(tv5_ctx* ctx, void* stream, const float* flow, int B, int H, int W,
                        const float* Kinv, int mode, int margin, const void* pts,
                        const int64_t* pt_offsets, double* x1_out, double* x2_out) {
+  TV5_LOCK(ctx);
   if (!ctx || !flow || B < 1 || H < 1 || W < 1 || !Kinv || mode < 0 || mode > 2 || !x1_out || !x2_out)
     return TV5_ERR_INVALID;
   if (mode != kFlowCrop && !pts) return TV5_ERR_INVALID;
@@ -2125,6 +2147,7 @@ int tv5_pose_from_flow(tv5_ctx* ctx, void* stream, const float* flow, int B, int
                        const int64_t* pt_offsets, const int32_t* sets, int iters, double thr,
                        int with_cheirality, float* E32_out, float* P32_out, tv5_result* result,
                        double* E_out, double* P_out) {
+  TV5_LOCK(ctx);
   if (!ctx || B < 1 || !result || (!E32_out && !E_out)) return TV5_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -2157,6 +2180,7 @@ int tv5_pose_from_flow(tv5_ctx* ctx, void* stream, const float* flow, int B, int
 int tv5_plane_sweep(tv5_ctx* ctx, void* stream, const float* ref_feat, const float* tgt_feat,
                     const float* pose, const float* K, const float* Kinv, int B, int C, int h, int w,
                     int nlabel, float mindepth, int by_depth, float* cost) {
+  TV5_LOCK(ctx);
   if (!ctx || !ref_feat || !tgt_feat || !pose || !K || !Kinv || !cost) return TV5_ERR_INVALID;
   if (B < 1 || C < 1 || h < 2 || w < 2 || nlabel < 1 || B > 65535 || nlabel > 65535) return TV5_ERR_INVALID;
   if ((int64_t)h * w > 0x3fffffff) return TV5_ERR_INVALID;
@@ -2171,6 +2195,7 @@ int tv5_plane_sweep(tv5_ctx* ctx, void* stream, const float* ref_feat, const flo
 
 int tv5_winner_record(tv5_ctx* ctx, void* stream, const double* E, const double* P,
                       const tv5_result* result, int set_offset, void* record_out) {
+  TV5_LOCK(ctx);
   if (!ctx || !E || !result || !record_out || set_offset < 0) return TV5_ERR_INVALID;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
   winner_record<<<1, 32, 0, (cudaStream_t)stream>>>(E, P, result, set_offset, (WinnerRecord*)record_out);
@@ -2180,6 +2205,7 @@ int tv5_winner_record(tv5_ctx* ctx, void* stream, const double* E, const double*
 
 int tv5_winner_pick(tv5_ctx* ctx, void* stream, const void* records, int G, double* E_out,
                     double* P_out, tv5_result* result_out) {
+  TV5_LOCK(ctx);
   if (!ctx || !records || G < 1 || !E_out || !result_out) return TV5_ERR_INVALID;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
   winner_pick<<<1, 32, 0, (cudaStream_t)stream>>>((const WinnerRecord*)records, G, E_out, P_out, result_out);
@@ -2188,6 +2214,7 @@ int tv5_winner_pick(tv5_ctx* ctx, void* stream, const void* records, int G, doub
 }
 
 int tv5_measure_fp32_peak(tv5_ctx* ctx, int mode, double* tflops_out) {
+  TV5_LOCK(ctx);
   if (!ctx || !tflops_out || mode < 0 || mode > 1) return TV5_ERR_INVALID;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
   float* sink = nullptr;
@@ -2217,6 +2244,7 @@ int tv5_measure_fp32_peak(tv5_ctx* ctx, int mode, double* tflops_out) {
 }
 
 int tv5_debug_guard(tv5_ctx* ctx, int on, int poison_byte) {
+  TV5_LOCK(ctx);
   if (!ctx) return TV5_ERR_INVALID;
   // only on a context that has not allocated anything yet: every buffer is then guarded
   if (ctx->ws.desc || ctx->ws.pp || ctx->ws.E_list || ctx->rng_u || ctx->ws.polish_jobs || ctx->ws.flow_jobs ||
@@ -2228,6 +2256,7 @@ int tv5_debug_guard(tv5_ctx* ctx, int on, int poison_byte) {
 }
 
 int tv5_debug_poison(tv5_ctx* ctx, int poison_byte) {
+  TV5_LOCK(ctx);
   if (!ctx || !ctx->guard) return TV5_ERR_INVALID;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
   TV5_CUDA(ctx, cudaDeviceSynchronize());
@@ -2242,6 +2271,7 @@ int tv5_debug_poison(tv5_ctx* ctx, int poison_byte) {
 }
 
 int tv5_debug_check_guards(tv5_ctx* ctx, int64_t* corrupted_bytes_out, int32_t* n_buffers_out) {
+  TV5_LOCK(ctx);
   if (!ctx || !corrupted_bytes_out) return TV5_ERR_INVALID;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
   TV5_CUDA(ctx, cudaDeviceSynchronize());
@@ -2266,6 +2296,7 @@ int tv5_debug_check_guards(tv5_ctx* ctx, int64_t* corrupted_bytes_out, int32_t* 
 }
 
 int tv5_debug_stray_write(tv5_ctx* ctx, int back) {
+  TV5_LOCK(ctx);
   if (!ctx || !ctx->guard || ctx->guards.empty()) return TV5_ERR_INVALID;
   TV5_CUDA(ctx, cudaSetDevice(ctx->device));
   const GuardRec& g = ctx->guards.front();
@@ -2275,18 +2306,21 @@ int tv5_debug_stray_write(tv5_ctx* ctx, int back) {
 }
 
 int tv5_set_force_exact(tv5_ctx* ctx, int on) {
+  TV5_LOCK(ctx);
   if (!ctx) return TV5_ERR_INVALID;
   ctx->force_exact = on != 0;
   return TV5_OK;
 }
 
 int tv5_set_graphs(tv5_ctx* ctx, int on) {
+  TV5_LOCK(ctx);
   if (!ctx) return TV5_ERR_INVALID;
   ctx->use_graphs = on != 0;
   return TV5_OK;
 }
 
 int tv5_set_early_exit(tv5_ctx* ctx, int on) {
+  TV5_LOCK(ctx);
   if (!ctx) return TV5_ERR_INVALID;
   ctx->early_exit = on != 0;
   // development knob: TV5_EARLY_FRAC="0.3,0.52" = interior stage boundaries
@@ -2309,18 +2343,21 @@ int tv5_set_early_exit(tv5_ctx* ctx, int on) {
 }
 
 int tv5_set_split_solver(tv5_ctx* ctx, int on) {
+  TV5_LOCK(ctx);
   if (!ctx) return TV5_ERR_INVALID;
   ctx->split_solver = on != 0;
   return TV5_OK;
 }
 
 int tv5_set_overlap(tv5_ctx* ctx, int on) {
+  TV5_LOCK(ctx);
   if (!ctx) return TV5_ERR_INVALID;
   ctx->overlap = on != 0;
   return TV5_OK;
 }
 
 int tv5_profile_enable(tv5_ctx* ctx, int on) {
+  TV5_LOCK(ctx);
   if (!ctx) return TV5_ERR_INVALID;
   profile_collect(ctx);
   ctx->profiling = on != 0;
@@ -2329,6 +2366,7 @@ int tv5_profile_enable(tv5_ctx* ctx, int on) {
 
 int tv5_profile_read(tv5_ctx* ctx, double ms_out[TV5_N_STAGES], int64_t launches_out[TV5_N_STAGES],
                      int reset) {
+  TV5_LOCK(ctx);
   if (!ctx) return TV5_ERR_INVALID;
   cudaSetDevice(ctx->device);
   profile_collect(ctx);

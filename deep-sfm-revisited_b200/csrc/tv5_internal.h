@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/tv5.h"
@@ -131,6 +132,7 @@ struct GuardRec { void* user; void* base; size_t bytes; size_t payload; };   // 
 }  // namespace tv5
 
 struct tv5_ctx {
+  std::recursive_mutex mu;               // held by every entry point: host threads sharing a context are serialised
   int device = 0;
   int sm_count = 0;
   int last_cuda = 0;

@@ -49,8 +49,9 @@ typedef struct tv5_ctx tv5_ctx;
 /* Per-device context: owns the workspace (grown on demand, never shrunk) and the cached
  * reference-RNG index tables.  No global state — replaces the reference's module-level
  * __constant__ parameters (kernel_functions.cu:16-20) and its per-call cudaMallocManaged /
- * cudaFree (essential_matrix.cu:222-274).  A context may be used from one host thread at a
- * time; different contexts are independent.  One context owns one workspace: submissions made on
+ * cudaFree (essential_matrix.cu:222-274).  Every entry point holds the context's mutex for the
+ * duration of the call, so host threads sharing a context are serialised (never racing); different
+ * contexts are independent.  One context owns one workspace: submissions made on
  * different streams are ordered inside the library (the later one first waits for the completion
  * event of the earlier one), so they never overlap on the device; use one context per stream for
  * concurrency.  If growing the workspace fails (TV5_ERR_NOMEM) the context stays usable: the next

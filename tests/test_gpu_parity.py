@@ -1074,6 +1074,43 @@ def test_submissions_on_two_streams_of_one_context_do_not_race(engine, std_pair)
         assert torch.equal(got.stats[:5], want.stats[:5])
 
 
+def test_two_host_threads_sharing_one_context_are_serialised(engine, std_pair):
+    """ctypes releases the GIL during a call, so two Python threads can be inside libtv5 at once.  Every
+    entry point holds the context's mutex: the calls are serialised, results equal the serial ones."""
+    import threading
+    sc, x1, x2 = std_pair
+    jobs = []
+    for k in range(2):
+        a = x1[k * 3000:k * 3000 + 5000].contiguous()
+        b = x2[k * 3000:k * 3000 + 5000].contiguous()
+        st = dev(synth.make_sets(5000, 1024, 90 + k), torch.int32)
+        jobs.append((a, b, st, engine.compute_pose(a, b, 2, THR, sets=st, want_mask=True)))
+    torch.cuda.synchronize()
+    out = [[], []]
+    errs = []
+
+    def work(k):
+        try:
+            a, b, st, _ = jobs[k]
+            for _ in range(40):
+                out[k].append(engine.compute_pose(a, b, 2, THR, sets=st, want_mask=True))
+        except Exception as ex:   # noqa: BLE001
+            errs.append(ex)
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errs, errs
+    for k in range(2):
+        want = jobs[k][3]
+        assert len(out[k]) == 40
+        for got in out[k]:
+            assert torch.equal(got.E, want.E) and torch.equal(got.P, want.P) and torch.equal(got.mask, want.mask)
+            assert torch.equal(got.stats[:5], want.stats[:5])
+
+
 def test_early_exit_single_large_pair_with_graph_replay(engine):
     """One large pair is staged too (enough work) and, as a single-pair submission, goes through the
     CUDA-graph replay: four identical calls with early exit == the full scoring."""
