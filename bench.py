@@ -419,10 +419,13 @@ K = torch.from_numpy(sc["K"])[None]
 orig_cp = ref.sfmnet_mod.compute_P_matrix_ransac
 out = {}
 backends = ["tv5"] + (["refext"] if harness.refext_path() else [])
-for variant in ("random_init_dicl", "synthetic_flow"):
+zero0, zero1 = torch.zeros_like(im0), torch.zeros_like(im1)     # textureless: SIFT finds nothing -> dense crop branch
+for variant in ("random_init_dicl", "synthetic_flow", "dense_fallback"):
     net = ref.make_sfmnet(128, seed=0)
-    if variant == "synthetic_flow":
+    if variant != "random_init_dicl":
         net.flow_estimator = FixedFlow(sc["flow"]).cuda()
+    in0, in1 = (zero0, zero1) if variant == "dense_fallback" else (im0, im1)
+    n_rep = 1 if variant == "dense_fallback" else reps
     rec = {"flow_ms": [], "pose_stage_ms": [], "computeP_ms": [], "depth_ms": []}
     calls = []
     def wrap(fn, key):
@@ -446,19 +449,19 @@ for variant in ("random_init_dicl", "synthetic_flow"):
     for be in backends:
         ref.use_backend(be)
         tot = []
-        for r in range(reps + 1):
+        for r in range(n_rep + 1):
             for k in rec: rec[k].clear()
             calls.clear()
             torch.cuda.synchronize(); t0 = time.perf_counter()
             with torch.no_grad():
-                flow, P, depth, _ = net(im0, im1, K, None, None, False, H, W)     # main.py:533
+                flow, P, depth, _ = net(in0, in1, K, None, None, False, H, W)     # main.py:533
             torch.cuda.synchronize(); tot.append((time.perf_counter() - t0) * 1e3)
         Pn = P[0, 0].double().cpu().numpy()
         res[be] = {"total_ms": float(np.median(tot[1:])), **{k: float(np.median(v)) for k, v in rec.items()},
                    "n_correspondences": int(calls[-1][0].shape[0]), "inliers": calls[-1][2],
                    "depth_finite": bool(torch.isfinite(depth).all())}
         res[be]["_P"], res[be]["_d"], res[be]["_c"] = Pn, depth.float().cpu(), calls[-1][:2]
-    if variant == "synthetic_flow":
+    if variant != "random_init_dicl":
         P0 = res["tv5"]["_P"]
         res["pose_error_vs_ground_truth_deg"] = {"rot": synth.rotation_error_deg(P0[:, :3], sc["R"]),
                                                  "trans": synth.translation_error_deg(P0[:, 3], sc["t"])}
@@ -478,7 +481,9 @@ out["workload"] = ("models/SFMnet.py:95-172 unmodified (staged copy), eval, b=1,
                    "(cfgs/kitti.yml, MIXED_PREC off), synthetic textured 370x1226 pair padded to 384x1280, cv2 SIFT+FLANN on the host; "
                    "pose_stage_ms = pose_by_ransac incl. SIFT/FLANN on the CPU, computeP_ms = compute_P_matrix_ransac + int(n) alone; "
                    "synthetic_flow: the flow network replaced by the scene's flow field (random-init DICL outputs noise, a few "
-                   "dozen inliers and many tied hypotheses, so the pose is only comparable between backends when it is well posed)")
+                   "dozen inliers and many tied hypotheses, so the pose is only comparable between backends when it is well posed); "
+                   "dense_fallback: textureless images, no SIFT keypoints -> pose_by_ransac's dense branch (SFMnet.py:239-241), "
+                   "422,100 correspondences in one computeP call, scene flow as in synthetic_flow")
 print("RESULT " + json.dumps(out))
 '''
 

@@ -198,7 +198,7 @@ def _forward(net, sc):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["synthetic_flow", "random_init_dicl"])
+@pytest.mark.parametrize("variant", ["synthetic_flow", "random_init_dicl", "dense_fallback"])
 def test_sfmnet_forward_dropin_vs_reference_extension(ref_mods, variant):
     """The reference's SFMnet eval forward, b = 1, nlabel = 128, random-init DICL + PSNet, on a
     synthetic KITTI-shaped textured pair (cv2 SIFT + FLANN run as in the reference), once with the
@@ -211,16 +211,21 @@ def test_sfmnet_forward_dropin_vs_reference_extension(ref_mods, variant):
       many near-tied hypotheses): the two solvers round E differently, so another of the tied
       hypotheses may win — the inlier counts must agree within 3 on identical inputs, and
       where the same hypothesis wins the depth maps agree.
+    * `dense_fallback`: textureless images, so SIFT finds no keypoints and `pose_by_ransac` takes its
+      other branch (models/SFMnet.py:239-241): every pixel of the `margin:-margin` crop, 422,100
+      correspondences, in one `computeP` call; scene flow as in `synthetic_flow`, same assertions.
     MIXED_PREC is switched off: under fp16 autocast the random-init 3-D convolutions overflow to
     NaN with either backend."""
     import scene
     sc = scene.make_scene(0)
     H, W = sc["ref"].shape[1:]
+    if variant == "dense_fallback":
+        sc = dict(sc, ref=np.zeros_like(sc["ref"]), target=np.zeros_like(sc["target"]))
     harness.load_reference("tv5", overrides={"MIXED_PREC": False})
     det = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
     torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
     net = ref_mods.make_sfmnet(128, seed=0)
-    if variant == "synthetic_flow":
+    if variant != "random_init_dicl":
         net.flow_estimator = _FixedFlow(sc["flow"], (int(np.ceil(H / 128) * 128), int(np.ceil(W / 128) * 128))).cuda()
     calls = []
     orig = ref_mods.sfmnet_mod.compute_P_matrix_ransac
@@ -247,7 +252,9 @@ def test_sfmnet_forward_dropin_vs_reference_extension(ref_mods, variant):
     P0, d0, c1_0, c2_0, n0 = res["tv5"]
     assert np.isfinite(P0).all() and abs(np.linalg.det(P0[:, :3]) - 1.0) < 1e-5
     assert torch.isfinite(d0).all() and c1_0.shape[0] >= 20 and n0 > 0
-    if variant == "synthetic_flow":
+    if variant == "dense_fallback":
+        assert c1_0.shape[0] == (H - 20) * (W - 20)                # the dense crop, margin 10
+    if variant != "random_init_dicl":
         # cfg.RESCALE_DEPTH scales the translation column in place by NORM_TARGET (models/PSNet.py:135)
         assert synth.rotation_error_deg(P0[:, :3], sc["R"]) < 0.05
         assert synth.translation_error_deg(P0[:, 3], sc["t"]) < 1.0
@@ -256,7 +263,7 @@ def test_sfmnet_forward_dropin_vs_reference_extension(ref_mods, variant):
         same_inputs = torch.equal(c1_0, c1_1) and torch.equal(c2_0, c2_1)
         dR = synth.rotation_error_deg(P0[:, :3], P1[:, :3])
         dt = synth.translation_error_deg(P0[:, 3], P1[:, 3])
-        if variant == "synthetic_flow":
+        if variant != "random_init_dicl":
             assert same_inputs and n0 == n1
             assert dR < 1e-3 and dt < 1e-3
             assert torch.allclose(d0, d1, rtol=1e-3, atol=1e-3)
